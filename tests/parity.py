@@ -1,0 +1,64 @@
+"""Parity metrics shared by the oracle-vs-golden and CUDA-vs-oracle tests.
+
+Tolerances are BASELINE.json's north_star: ternary codes agree on >= 99.9 % of entries;
+per-row scales within 1e-4 relative (judged on (row, block) pairs whose codes agree, since
+one flipped code moves that row's alpha by ~1 %); layer reconstruction
+error within 1e-3 relative.
+"""
+
+import numpy as np
+
+CODE_AGREEMENT = 0.999
+SCALE_RTOL = 1e-4
+RECON_RTOL = 1e-3
+
+
+def code_agreement(Ta, Tb):
+    Ta = np.asarray(Ta).astype(np.int8)
+    Tb = np.asarray(Tb).astype(np.int8)
+    assert Ta.shape == Tb.shape
+    return float((Ta == Tb).mean())
+
+
+def block_pairs_agree(Ta, Tb, perm, block_size):
+    """Boolean (n, nb): True where all codes of (row, block) agree."""
+    Ta = np.asarray(Ta).astype(np.int8)
+    Tb = np.asarray(Tb).astype(np.int8)
+    n, m = Ta.shape
+    nb = (m + block_size - 1) // block_size
+    out = np.zeros((n, nb), dtype=bool)
+    for k in range(nb):
+        cols = np.asarray(perm[k * block_size:(k + 1) * block_size])
+        out[:, k] = (Ta[:, cols] == Tb[:, cols]).all(axis=1)
+    return out
+
+
+def scale_rel_err(a, b, mask=None, floor=0.0):
+    """max |a-b| / max(|b|, floor) over ``mask``.  ``floor`` is the absolute scale below which a
+    quantity is compared absolutely: mu is an OFFSET that sits near zero for zero-mean weights, so
+    its error is judged relative to the row's step alpha (pass floor=|alpha|)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    den = np.maximum(np.abs(b), floor)
+    den = np.where(den == 0, 1.0, den)
+    err = np.abs(a - b) / den
+    if mask is not None:
+        if not mask.any():
+            return 0.0
+        err = err[mask]
+    return float(err.max()) if err.size else 0.0
+
+
+def assert_layer_parity(got, ref, block_size=128, same_perm_required=True, what=""):
+    """got/ref: dicts with alpha, mu, T, perm."""
+    if same_perm_required:
+        assert np.array_equal(np.asarray(got["perm"]), np.asarray(ref["perm"])), f"{what}: perm differs"
+    agree = code_agreement(got["T"], ref["T"])
+    assert agree >= CODE_AGREEMENT, f"{what}: code agreement {agree:.6f} < {CODE_AGREEMENT}"
+    if np.array_equal(np.asarray(got["perm"]), np.asarray(ref["perm"])):
+        mask = block_pairs_agree(got["T"], ref["T"], ref["perm"], block_size)
+        ea = scale_rel_err(got["alpha"], ref["alpha"], mask)
+        em = scale_rel_err(got["mu"], ref["mu"], mask, floor=np.abs(np.asarray(ref["alpha"], dtype=np.float64)))
+        assert ea <= SCALE_RTOL, f"{what}: alpha rel err {ea:.3e} > {SCALE_RTOL}"
+        assert em <= SCALE_RTOL, f"{what}: mu err (relative to alpha) {em:.3e} > {SCALE_RTOL}"
+    return agree
