@@ -1,0 +1,157 @@
+// A9-A11: un-permute the sweep-order codes into original column positions (gptq.py:155), dequantise
+// (gptq.py:201-230), and the 2-bit codec (utils.py:189-248).  Byte/integer work, HBM-bound: one thread
+// per output byte group, 128-bit accesses on the contiguous side.
+#include "common.cuh"
+
+namespace tq {
+
+__global__ void __launch_bounds__(256)
+unpermute_kernel(const int8_t* __restrict__ Tperm, int n, int m, const int32_t* __restrict__ perm,
+                 int8_t* __restrict__ Torig, float* __restrict__ Tf32) {
+    // scatter form: thread handles sweep position p of row r.  Rows are 4-11 KB, so a CTA's writes
+    // to one row merge in L2 before eviction.
+    const int r = blockIdx.y;
+    const int8_t* src = Tperm + (int64_t)r * m;
+    int8_t* dst = Torig + (int64_t)r * m;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < m; p += gridDim.x * blockDim.x) {
+        const int c = perm[p];
+        const int8_t v = src[p];
+        dst[c] = v;
+        if (Tf32) Tf32[(int64_t)r * m + c] = (float)v;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+dequant_kernel(const float* __restrict__ alpha, const float* __restrict__ mu, int nb, const int8_t* __restrict__ Torig,
+               int n, int m, const int32_t* __restrict__ perm, int block, float* __restrict__ Wq) {
+    const int r = blockIdx.y;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < m; p += gridDim.x * blockDim.x) {
+        const int k = p / block;
+        const int c = perm[p];
+        const float a = alpha[(int64_t)r * nb + k], u = mu[(int64_t)r * nb + k];
+        Wq[(int64_t)r * m + c] = __fadd_rn(__fmul_rn(a, (float)Torig[(int64_t)r * m + c]), u);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack2b_kernel(const T* __restrict__ in, int64_t count, uint8_t* __restrict__ out) {
+    const int64_t nbytes = (count + 3) / 4;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nbytes; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t base = q * 4;
+        unsigned byte = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t i = base + k;
+            const unsigned code = (i < count) ? (unsigned)((int)in[i] + 1) & 3u : 0u;   // zero pad (utils.py:207-209)
+            byte |= code << (2 * k);
+        }
+        out[q] = (uint8_t)byte;
+    }
+}
+
+// vector path: 16 int8 codes -> one 32-bit word of packed output per thread
+__global__ void __launch_bounds__(256)
+pack2b_vec_kernel(const int4* __restrict__ in, int64_t groups, uint32_t* __restrict__ out) {
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+        const int4 v = in[g];
+        const uint32_t wv[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+        uint32_t word = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            // four int8 codes in wv[q]: keep 2 bits (-1 -> 3), +1 per byte (max 4, no carry), keep 2 bits again
+            const uint32_t c = ((wv[q] & 0x03030303u) + 0x01010101u) & 0x03030303u;
+            const uint32_t byte = (c & 3u) | ((c >> 6) & 0xCu) | ((c >> 12) & 0x30u) | ((c >> 18) & 0xC0u);
+            word |= byte << (8 * q);
+        }
+        out[g] = word;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+unpack2b_kernel(const uint8_t* __restrict__ in, int64_t count, int8_t* __restrict__ out) {
+    const int64_t nbytes = (count + 3) / 4;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nbytes; q += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned byte = in[q];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int64_t i = q * 4 + k;
+            if (i < count) out[i] = (int8_t)((int)((byte >> (2 * k)) & 3u) - 1);
+        }
+    }
+}
+
+static inline unsigned grid_for(int64_t work, int threads) {
+    int64_t g = ceil_div(work, threads);
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+int launch_unpermute(const int8_t* Tperm, int64_t n, int64_t m, const int32_t* perm, int8_t* Torig, float* Tf32,
+                     cudaStream_t st) {
+    dim3 grid((unsigned)(ceil_div(m, 256) < 64 ? ceil_div(m, 256) : 64), (unsigned)n);
+    unpermute_kernel<<<grid, 256, 0, st>>>(Tperm, (int)n, (int)m, perm, Torig, Tf32);
+    TQ_LAUNCH_CHECK("unpermute_kernel");
+    return 0;
+}
+
+}  // namespace tq
+
+extern "C" int tq_unpermute_codes(const int8_t* Tperm, int64_t n, int64_t m, const int32_t* perm, int8_t* Torig,
+                                  float* Tf32, void* stream) {
+    using namespace tq;
+    TQ_CHECK_ARG(Tperm && perm && Torig && n > 0 && m > 0 && n <= 65535 * 1024, "tq_unpermute_codes: bad arguments");
+    TQ_CHECK_ARG(Tperm != Torig, "tq_unpermute_codes: in-place not supported");
+    return launch_unpermute(Tperm, n, m, perm, Torig, Tf32, (cudaStream_t)stream);
+}
+
+extern "C" int tq_dequant(const float* alpha, const float* mu, int64_t nb, const int8_t* Torig, int64_t n, int64_t m,
+                          const int32_t* perm, int64_t block, float* Wq, void* stream) {
+    using namespace tq;
+    TQ_CHECK_ARG(alpha && mu && Torig && perm && Wq && n > 0 && m > 0 && block > 0, "tq_dequant: bad arguments");
+    TQ_CHECK_ARG(nb == ceil_div(m, block), "tq_dequant: nb must equal ceil(m / block)");
+    dim3 grid((unsigned)(ceil_div(m, 256) < 64 ? ceil_div(m, 256) : 64), (unsigned)n);
+    dequant_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(alpha, mu, (int)nb, Torig, (int)n, (int)m, perm, (int)block, Wq);
+    TQ_LAUNCH_CHECK("dequant_kernel");
+    return 0;
+}
+
+extern "C" int tq_pack2b(const int8_t* T, int64_t count, uint8_t* packed, void* stream) {
+    using namespace tq;
+    TQ_CHECK_ARG(T && packed && count >= 0, "tq_pack2b: bad arguments");
+    if (count == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(T) & 15) == 0) && ((reinterpret_cast<uintptr_t>(packed) & 3) == 0);
+    const int64_t groups = aligned ? count / 16 : 0;
+    if (groups > 0) {
+        pack2b_vec_kernel<<<grid_for(groups, 256), 256, 0, st>>>(reinterpret_cast<const int4*>(T), groups,
+                                                                 reinterpret_cast<uint32_t*>(packed));
+        TQ_LAUNCH_CHECK("pack2b_vec_kernel");
+    }
+    const int64_t done = groups * 16;
+    if (done < count) {
+        pack2b_kernel<int8_t><<<grid_for((count - done + 3) / 4, 256), 256, 0, st>>>(T + done, count - done, packed + done / 4);
+        TQ_LAUNCH_CHECK("pack2b_kernel");
+    }
+    return 0;
+}
+
+extern "C" int tq_pack2b_f32(const float* T, int64_t count, uint8_t* packed, void* stream) {
+    using namespace tq;
+    TQ_CHECK_ARG(T && packed && count >= 0, "tq_pack2b_f32: bad arguments");
+    if (count == 0) return 0;
+    pack2b_kernel<float><<<grid_for((count + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(T, count, packed);
+    TQ_LAUNCH_CHECK("pack2b_kernel<float>");
+    return 0;
+}
+
+extern "C" int tq_unpack2b(const uint8_t* packed, int64_t count, int8_t* T, void* stream) {
+    using namespace tq;
+    TQ_CHECK_ARG(T && packed && count >= 0, "tq_unpack2b: bad arguments");
+    if (count == 0) return 0;
+    unpack2b_kernel<<<grid_for((count + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(packed, count, T);
+    TQ_LAUNCH_CHECK("unpack2b_kernel");
+    return 0;
+}

@@ -1,0 +1,369 @@
+// A2 (tensor-core path): H += X'X as a TMA-fed tcgen05 SYRK with fp32 accumulators in TMEM.
+// Reference: gptq.py:59-76 (`self.H += inp @ inp.t()`, inp = X'), main.py:128.
+//
+// X is token-major [Nt, m] fp16/bf16, so with K = tokens BOTH operands of H = X'X are "MN-major"
+// slabs of the same tensor: one 2-D tensor map serves A (128 columns) and B (256 columns).
+//
+//   tile      : 128 (rows of H) x 256 (cols of H) per CTA, UMMA 128x256x16, cta_group::1
+//   pipeline  : 4 smem stages of 64 tokens (A 16 KB + B 32 KB, 128B-swizzled TMA boxes of 64 cols x 64 tokens)
+//   TMEM      : 2 accumulators x 256 columns (all 512) so the epilogue of item i overlaps the MMAs of i+1
+//   epilogue  : tcgen05.ld 32 columns -> swizzled smem -> TMA reduce-add (fp32 add in L2) into H;
+//               this is the reference's `H +=`, and it lets several token chunks of one tile be
+//               in flight on different SMs with no ordering between them
+//   schedule  : persistent, one CTA per SM; work item = (token chunk, tile), chunk-major so that the
+//               X rows of the current chunk (<= ~40 MB) stay L2-resident while all tiles consume them;
+//               only tiles that touch the upper triangle are computed (tq_symmetrize mirrors later)
+//   roles     : warp 0 TMA producer, warp 1 MMA issuer (one thread), warp 2 TMEM allocator,
+//               warps 4-7 epilogue (TMEM lane quarter = warp % 4)
+#include "common.cuh"
+
+#include <cuda.h>
+
+namespace tq {
+
+constexpr int HT_BM = 128, HT_BN = 256, HT_BK = 64, HT_STAGES = 4, HT_UMMA_K = 16;
+constexpr int HT_A_BYTES = HT_BM * HT_BK * 2;              // 16384
+constexpr int HT_B_BYTES = HT_BN * HT_BK * 2;              // 32768
+constexpr int HT_STAGE_BYTES = HT_A_BYTES + HT_B_BYTES;    // 49152
+constexpr int HT_BOX_BYTES = 64 * HT_BK * 2;               // one TMA box: 64 columns x 64 tokens = 8192
+constexpr int HT_EPI_COLS = 32;
+constexpr int HT_EPI_BYTES = HT_BM * HT_EPI_COLS * 4;      // 16384
+constexpr int HT_EPI_STAGES = 2;
+constexpr int HT_THREADS = 256;
+constexpr int HT_SMEM = HT_STAGES * HT_STAGE_BYTES + HT_EPI_STAGES * HT_EPI_BYTES + 256 + 1024;
+constexpr unsigned long long HT_SPIN_LIMIT = 4000000000ull;  // ~2 s of SM clocks: trap instead of hanging the box
+
+__device__ int g_ht_timeout_flag = 0;
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > HT_SPIN_LIMIT) {
+            atomicExch(&g_ht_timeout_flag, 1);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// smem matrix descriptor for an MN-major, 128B-swizzled operand slab made of [64 cols x 64 tokens] TMA boxes:
+//   8 token rows x 128 B = one 1024 B swizzle atom; next 8 tokens at +1024 B (SBO); next 64 columns at +8192 B (LBO)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(HT_BOX_BYTES >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           (1ull << 46) | (2ull << 61);
+}
+
+struct TileSched {
+    int nbi, nbj, tiles;
+    __device__ __forceinline__ void decode(int t, int& bi, int& bj) const {
+        int j = 0;
+        for (;; ++j) {
+            const int cnt = min(nbi, 2 * j + 2);      // row blocks of column block j that touch the upper triangle
+            if (t < cnt) break;
+            t -= cnt;
+        }
+        bi = t;
+        bj = j;
+    }
+};
+
+__global__ void __launch_bounds__(HT_THREADS, 1)
+hessian_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_h,
+                  int Nt, int kc, int num_chunks, TileSched sched, uint32_t idesc) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_epi = s_base + HT_STAGES * HT_STAGE_BYTES;
+    const uint32_t s_bar = s_epi + HT_EPI_STAGES * HT_EPI_BYTES;
+    auto full_bar = [&](int s) { return s_bar + 8 * s; };
+    auto empty_bar = [&](int s) { return s_bar + 8 * (HT_STAGES + s); };
+    auto tfull_bar = [&](int a) { return s_bar + 8 * (2 * HT_STAGES + a); };
+    auto tempty_bar = [&](int a) { return s_bar + 8 * (2 * HT_STAGES + 2 + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + HT_STAGES * HT_STAGE_BYTES + HT_EPI_STAGES * HT_EPI_BYTES + 8 * (2 * HT_STAGES + 4));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_h) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < HT_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_items = num_chunks * sched.tiles;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        int stage = 0, phase = 0;
+        for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
+            const int chunk = it / sched.tiles;
+            int bi, bj;
+            sched.decode(it - chunk * sched.tiles, bi, bj);
+            const int t0 = chunk * kc;
+            const int t1 = min(Nt, t0 + kc);
+            const int nkb = (t1 - t0 + HT_BK - 1) / HT_BK;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1);
+                const uint32_t sa = s_base + stage * HT_STAGE_BYTES;
+                const uint32_t sb = sa + HT_A_BYTES;
+                mbar_expect_tx(full_bar(stage), HT_STAGE_BYTES);
+                const int tok = t0 + kb * HT_BK;
+#pragma unroll
+                for (int c = 0; c < HT_BM / 64; ++c) tma_load_2d(sa + c * HT_BOX_BYTES, &map_x, full_bar(stage), bi * HT_BM + c * 64, tok);
+#pragma unroll
+                for (int c = 0; c < HT_BN / 64; ++c) tma_load_2d(sb + c * HT_BOX_BYTES, &map_x, full_bar(stage), bj * HT_BN + c * 64, tok);
+                if (++stage == HT_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer =====
+        int stage = 0, phase = 0, n_item = 0;
+        for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++n_item) {
+            const int chunk = it / sched.tiles;
+            const int t0 = chunk * kc;
+            const int t1 = min(Nt, t0 + kc);
+            const int nkb = (t1 - t0 + HT_BK - 1) / HT_BK;
+            const int acc = n_item & 1;
+            mbar_wait(tempty_bar(acc), ((n_item >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * HT_BN;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                const uint32_t sa = s_base + stage * HT_STAGE_BYTES;
+                const uint32_t sb = sa + HT_A_BYTES;
+#pragma unroll
+                for (int k = 0; k < HT_BK / HT_UMMA_K; ++k) {
+                    const uint64_t ad = make_desc(sa + k * HT_UMMA_K * 128);
+                    const uint64_t bd = make_desc(sb + k * HT_UMMA_K * 128);
+                    umma_f16(tmem_d, ad, bd, idesc, (kb | k) != 0);
+                }
+                umma_commit(empty_bar(stage));          // frees the smem slot once these MMAs have read it
+                if (kb == nkb - 1) umma_commit(tfull_bar(acc));
+                if (++stage == HT_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> swizzled smem -> TMA reduce-add into H =====
+        const int q = warp & 3;                          // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;                   // row of the 128-row tile
+        const bool leader = (warp == 4 && lane == 0);
+        int n_item = 0, estage = 0;
+        for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++n_item) {
+            const int chunk = it / sched.tiles;
+            int bi, bj;
+            sched.decode(it - chunk * sched.tiles, bi, bj);
+            const int acc = n_item & 1;
+            mbar_wait(tfull_bar(acc), (n_item >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * HT_BN;
+            for (int cg = 0; cg < HT_BN / HT_EPI_COLS; ++cg) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + cg * HT_EPI_COLS, v);
+                tmem_ld_wait();
+                if (cg == HT_BN / HT_EPI_COLS - 1) {     // accumulator fully read: hand it back to the MMA warp
+                    tc_fence_before();
+                    mbar_arrive(tempty_bar(acc));
+                }
+                // staging buffer `estage` must have been read by the TMA store issued two groups ago
+                if (leader) bulk_wait_read<HT_EPI_STAGES - 1>();
+                named_bar_sync(1, 128);
+                const uint32_t sdst = s_epi + estage * HT_EPI_BYTES + row * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t a = sdst + ((c ^ (row & 7)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * c]), "r"(v[4 * c + 1]),
+                                 "r"(v[4 * c + 2]), "r"(v[4 * c + 3])
+                                 : "memory");
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, 128);
+                if (leader) {
+                    tma_reduce_add_2d(&map_h, s_epi + estage * HT_EPI_BYTES, bj * HT_BN + cg * HT_EPI_COLS, bi * HT_BM);
+                    bulk_commit();
+                }
+                estage ^= 1;
+            }
+        }
+        if (leader) bulk_wait_read<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled encode_fn() {
+    static PFN_tmapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+    }
+    return fn;
+}
+
+int hessian_accum_tcgen05(float* H, int64_t ldh, const void* X, int64_t Nt, int64_t m, int64_t ldx, int dtype,
+                          cudaStream_t st) {
+    PFN_tmapEncodeTiled enc = encode_fn();
+    if (!enc) {
+        set_error("tq_hessian_accum: cuTensorMapEncodeTiled not available from the driver");
+        return TQ_E_UNSUPPORTED;
+    }
+    TQ_CHECK_ARG(Nt < (1ll << 31) && m < (1ll << 31), "tq_hessian_accum: sizes exceed the TMA coordinate range");
+
+    CUtensorMap map_x, map_h;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)m, (cuuint64_t)Nt};
+        cuuint64_t strides[1] = {(cuuint64_t)ldx * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)HT_BK};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&map_x, dtype == TQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                         const_cast<void*>(X), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("tq_hessian_accum: cuTensorMapEncodeTiled(X) failed with CUresult %d", (int)r);
+            return TQ_E_BADARG;
+        }
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)m, (cuuint64_t)m};
+        cuuint64_t strides[1] = {(cuuint64_t)ldh * 4};
+        cuuint32_t box[2] = {(cuuint32_t)HT_EPI_COLS, (cuuint32_t)HT_BM};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = enc(&map_h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, H, dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("tq_hessian_accum: cuTensorMapEncodeTiled(H) failed with CUresult %d", (int)r);
+            return TQ_E_BADARG;
+        }
+    }
+
+    TileSched sched;
+    sched.nbi = (int)ceil_div(m, HT_BM);
+    sched.nbj = (int)ceil_div(m, HT_BN);
+    sched.tiles = 0;
+    for (int j = 0; j < sched.nbj; ++j) sched.tiles += (sched.nbi < 2 * j + 2) ? sched.nbi : 2 * j + 2;
+
+    // token chunk: small enough that chunk x m x 2 B stays L2-resident while every tile reads it,
+    // large enough to amortise the reduce-add epilogue, and giving >= ~6 work items per SM
+    const int sms = sm_count();
+    int64_t kc_l2 = (40ll << 20) / (2 * m);
+    kc_l2 = (kc_l2 / HT_BK) * HT_BK;
+    if (kc_l2 < 256) kc_l2 = 256;
+    if (kc_l2 > 8192) kc_l2 = 8192;
+    const int64_t want_chunks = ceil_div((int64_t)6 * sms, sched.tiles);
+    int64_t kc = ceil_div(ceil_div(Nt, want_chunks), HT_BK) * HT_BK;
+    if (kc < 256) kc = 256;
+    if (kc > kc_l2) kc = kc_l2;
+    const int64_t num_chunks = ceil_div(Nt, kc);
+    const int64_t items = num_chunks * sched.tiles;
+    TQ_CHECK_ARG(items < (1ll << 31), "tq_hessian_accum: too many work items");
+
+    const uint32_t fmt = (dtype == TQ_F16) ? 0u : 1u;
+    // tcgen05 instruction descriptor (kind::f16): D=f32, A/B format, A and B MN-major, N=256, M=128
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) |
+                           ((uint32_t)(HT_BN >> 3) << 17) | ((uint32_t)(HT_BM >> 4) << 24);
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        TQ_CUDA(cudaFuncSetAttribute(hessian_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM));
+        attr_set = true;
+    }
+    const int grid = (int)((items < sms) ? items : sms);
+    hessian_tc_kernel<<<grid, HT_THREADS, HT_SMEM, st>>>(map_x, map_h, (int)Nt, (int)kc, (int)num_chunks, sched, idesc);
+    TQ_LAUNCH_CHECK("hessian_tc_kernel");
+    return 0;
+}
+
+}  // namespace tq

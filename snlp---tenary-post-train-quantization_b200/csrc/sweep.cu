@@ -1,0 +1,136 @@
+// The whole-layer block column sweep: gptq.py:108-199 (main.py:143-223) as one host-side loop that
+// enqueues every block step on the caller's stream with no host synchronisation -- the reference's
+// per-block syncs (`.tolist()` gptq.py:133, `torch.equal` quantizer.py:164, `.item()` quantizer.py:218)
+// are gone: the permutation, the remaining-column list and the AGA vector all stay on the device.
+#include "common.cuh"
+
+namespace tq {
+
+int launch_atq_block(const float*, int64_t, int64_t, const int32_t*, int64_t, int64_t, const float*, int, int8_t*,
+                     int64_t, float*, float*, int64_t, float*, int64_t, int32_t*, cudaStream_t);
+int launch_aga_vector(const float*, int64_t, const int32_t*, int64_t, int64_t, int, float*, cudaStream_t);
+int launch_ssr_stats(const float*, int64_t, int64_t, const int32_t*, int64_t, float*, float*, cudaStream_t);
+int launch_ssr_select(const float*, int64_t, const float*, int64_t, const float*, const int32_t*, int64_t, int64_t,
+                      int32_t*, int32_t*, float*, uint32_t*, cudaStream_t);
+int launch_err_feedback(float*, int64_t, int64_t, const float*, int64_t, const float*, int64_t, const int32_t*,
+                        int64_t, int64_t, const int32_t*, int64_t, int64_t, cudaStream_t);
+int launch_unpermute(const int8_t*, int64_t, int64_t, const int32_t*, int8_t*, float*, cudaStream_t);
+
+__global__ void iota_kernel(int32_t* __restrict__ a, int m) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) a[i] = i;
+}
+
+struct SweepWs {
+    float* E;
+    float* rowmean;
+    float* partials;
+    float* sims;       // [2*m]: similarities + selection keys
+    float* s1d;
+    int32_t* rem[2];
+    int8_t* Tperm;
+    int64_t bytes;
+};
+
+static inline int64_t align256(int64_t x) { return (x + 255) & ~(int64_t)255; }
+
+static SweepWs carve(void* base, int64_t n, int64_t m, int64_t block) {
+    SweepWs w;
+    char* p = static_cast<char*>(base);
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) { char* q = p ? p + off : nullptr; off += align256(bytes); return q; };
+    const int64_t chunks = tq_ssr_num_chunks(n);
+    w.E = reinterpret_cast<float*>(take(sizeof(float) * n * block));
+    w.rowmean = reinterpret_cast<float*>(take(sizeof(float) * n));
+    w.partials = reinterpret_cast<float*>(take(sizeof(float) * chunks * 2 * m));
+    w.sims = reinterpret_cast<float*>(take(sizeof(float) * 2 * m));
+    w.s1d = reinterpret_cast<float*>(take(sizeof(float) * (block + 1)));
+    w.rem[0] = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * m));
+    w.rem[1] = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * m));
+    w.Tperm = reinterpret_cast<int8_t*>(take(n * m));
+    w.bytes = off;
+    return w;
+}
+
+}  // namespace tq
+
+extern "C" int64_t tq_sweep_workspace_bytes(int64_t n, int64_t m, int64_t block) {
+    return tq::carve(nullptr, n, m, block).bytes;
+}
+
+extern "C" int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const float* Hd, const float* Hraw,
+                              const float* Hinv, int64_t block, int order, int aga, int max_iter,
+                              const int32_t* static_perm, int8_t* Torig, float* alpha, float* mu, int32_t* perm,
+                              void* workspace, int64_t workspace_bytes, void* stream) {
+    using namespace tq;
+    TQ_CHECK_ARG(W && Hinv && Torig && alpha && mu && perm && workspace, "tq_sweep_layer: null pointer");
+    TQ_CHECK_ARG(n > 0 && m > 0 && ldw >= m && block >= 1 && block <= 512, "tq_sweep_layer: bad shape");
+    TQ_CHECK_ARG(order == TQ_ORDER_SEQUENTIAL || order == TQ_ORDER_SSR || order == TQ_ORDER_STATIC,
+                 "tq_sweep_layer: unknown order %d", order);
+    TQ_CHECK_ARG(order != TQ_ORDER_STATIC || static_perm != nullptr, "tq_sweep_layer: TQ_ORDER_STATIC needs static_perm");
+    TQ_CHECK_ARG(aga == TQ_AGA_NONE || (aga == TQ_AGA_HESSIAN && Hd) || (aga == TQ_AGA_ACTIVATIONS && Hraw),
+                 "tq_sweep_layer: AGA mode %d needs its Hessian (Hd for HESSIAN, Hraw for ACTIVATIONS)", aga);
+    TQ_CHECK_ARG(max_iter >= 0, "tq_sweep_layer: max_iter < 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    SweepWs ws = carve(workspace, n, m, block);
+    if (ws.bytes > workspace_bytes) {
+        set_error("tq_sweep_layer: workspace %lld bytes < required %lld", (long long)workspace_bytes, (long long)ws.bytes);
+        return TQ_E_WORKSPACE;
+    }
+    const int64_t nb = ceil_div(m, block);
+    const int64_t chunks = tq_ssr_num_chunks(n);
+    const float* Haga = (aga == TQ_AGA_HESSIAN) ? Hd : Hraw;
+    int rc;
+
+    if (order == TQ_ORDER_SSR) {
+        iota_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, st>>>(ws.rem[0], (int)m);
+        TQ_LAUNCH_CHECK("iota_kernel");
+    } else if (order == TQ_ORDER_SEQUENTIAL) {
+        iota_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, st>>>(perm, (int)m);
+        TQ_LAUNCH_CHECK("iota_kernel");
+    } else {
+        TQ_CUDA(cudaMemcpyAsync(perm, static_perm, sizeof(int32_t) * m, cudaMemcpyDeviceToDevice, st));
+    }
+
+    int cur = 0;
+    int64_t done = 0, rem = m;
+    for (int64_t k = 0; done < m; ++k) {
+        const int64_t b = (m - done < block) ? (m - done) : block;
+        const int32_t* blk_idx;
+        const int32_t* rem_idx;
+        if (order == TQ_ORDER_SSR) {
+            if (rem <= block) {                                   // reorder.py:125-126
+                TQ_CUDA(cudaMemcpyAsync(perm + done, ws.rem[cur], sizeof(int32_t) * rem, cudaMemcpyDeviceToDevice, st));
+            } else {
+                if ((rc = launch_ssr_stats(W, ldw, n, ws.rem[cur], rem, ws.rowmean, ws.partials, st))) return rc;
+                if ((rc = launch_ssr_select(ws.partials, chunks, ws.rowmean, n, nullptr, ws.rem[cur], rem, block,
+                                            perm + done, ws.rem[cur ^ 1], ws.sims,
+                                            reinterpret_cast<uint32_t*>(ws.sims + m), st)))
+                    return rc;
+                cur ^= 1;
+            }
+            rem -= b;
+            blk_idx = perm + done;
+            rem_idx = ws.rem[cur];
+        } else {
+            rem = m - done - b;
+            const bool contiguous = (order == TQ_ORDER_SEQUENTIAL);
+            blk_idx = contiguous ? nullptr : perm + done;
+            rem_idx = contiguous ? nullptr : perm + done + b;
+        }
+        const float* s1d = nullptr;
+        if (aga != TQ_AGA_NONE) {
+            if ((rc = launch_aga_vector(Haga, m, blk_idx, done, b, aga, ws.s1d, st))) return rc;
+            s1d = ws.s1d;
+        }
+        if ((rc = launch_atq_block(W, ldw, n, blk_idx, done, b, s1d, max_iter, ws.Tperm + done, m, alpha + k, mu + k,
+                                   nb, ws.E, block, nullptr, st)))
+            return rc;
+        if (rem > 0) {                                            // gptq.py:170 (and SURVEY Q3)
+            if ((rc = launch_err_feedback(W, ldw, n, ws.E, block, Hinv, m, blk_idx, done, b, rem_idx, done + b, rem, st)))
+                return rc;
+        }
+        done += b;
+    }
+    return launch_unpermute(ws.Tperm, n, m, perm, Torig, nullptr, st);
+}

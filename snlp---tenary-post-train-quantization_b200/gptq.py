@@ -1,0 +1,281 @@
+"""GPTQ layer quantizer with ATQ + SSR -- B200 mirror of the reference's ``gptq.py``
+(``/root/reference/gptq.py``: class ``GPTQ`` :21-230, ``GPTQQuantizer`` :233-272) and of the inline
+loop ``main.py`` really runs (``PT2LLMQuantizer.quantize_layer``, ``/root/reference/main.py:102-230``).
+
+Public surface is the reference's: ``GPTQ(layer, block_size, percdamp)``, ``add_batch(inp)``,
+``quantize(use_ssr) -> (alpha, mu, T, perm)``, ``get_quantized_weight()``; ``fasterquant`` is an alias
+of ``quantize`` (BASELINE north_star's name for it).  Underneath:
+
+  add_batch  -> tq_hessian_accum   TMA-fed tcgen05/TMEM SYRK, fp32 accumulate (fp16/bf16 activations);
+                                   fp32 activations take the CUDA-core fp32 SYRK
+  quantize   -> tq_hessian_finalize (scale + damp), tq_chol_inverse (potrf + potri), tq_sweep_layer
+                (per block: SSR select, AGA vector, fused ATQ fit + error, error-feedback GEMM),
+                all enqueued on the current stream with one host sync at the end (the Cholesky status)
+
+Everything runs on the layer's CUDA device; there is no CPU fallback.
+"""
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+try:
+    from . import _lib
+    from .quantizer import AsymmetricTernaryQuantizer  # noqa: F401  (re-exported like the reference)
+    from .reorder import SSRReorderer, select_next_block_ssr, compute_column_similarity_to_mean  # noqa: F401
+except ImportError:
+    import _lib
+    from quantizer import AsymmetricTernaryQuantizer  # noqa: F401
+    from reorder import SSRReorderer, select_next_block_ssr, compute_column_similarity_to_mean  # noqa: F401
+
+_AGA = {"none": _lib.AGA_NONE, "hessian": _lib.AGA_HESSIAN, "activations": _lib.AGA_ACTIVATIONS}
+
+
+class HessianState:
+    """Accumulated H = sum X'X for one layer INPUT, shareable between the linears that read the same
+    activations (q/k/v, gate/up) -- SURVEY 8f N1.  Holds the raw accumulator, the token count and a
+    cache of the damped matrix and its inverse per ``percdamp``."""
+
+    def __init__(self, columns: int, device):
+        self.columns = columns
+        self.device = torch.device(device)
+        self.H = torch.zeros((columns, columns), device=self.device, dtype=torch.float32)
+        self.nsamples = 0
+        self.hessian_path = _lib.HESS_AUTO
+        self._upper_only = False      # the tcgen05 path fills only tiles touching the upper triangle
+        self._cache = {}
+
+    def add_batch(self, inp: torch.Tensor):
+        lib = _lib.load()
+        _lib.require_cuda(inp, "inp")
+        if inp.dim() == 3:
+            inp = inp.reshape(-1, inp.shape[-1])               # gptq.py:68-69
+        if inp.dim() != 2 or inp.shape[1] != self.columns:
+            raise ValueError(f"add_batch: expected (..., {self.columns}) activations, got {tuple(inp.shape)}")
+        x = inp.detach()
+        if x.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+            x = x.float()
+        if x.stride(1) != 1 or (x.stride(0) * x.element_size()) % 16 != 0 or x.data_ptr() % 16 != 0:
+            x = x.contiguous()
+        nt = x.shape[0]
+        with torch.cuda.device(self.device):
+            _lib.check(lib.tq_hessian_accum(_lib.ptr(self.H), self.columns, _lib.ptr(x), nt, self.columns,
+                                            x.stride(0), _lib.dtype_code(x.dtype), self.hessian_path,
+                                            _lib.stream()), "tq_hessian_accum")
+        x.record_stream(torch.cuda.current_stream(self.device))
+        self._upper_only = True
+        self._cache.clear()
+        self.nsamples += nt                                     # gptq.py:76
+
+    def full(self) -> torch.Tensor:
+        """H as a full symmetric matrix (mirrors the upper triangle on first read)."""
+        if self._upper_only:
+            lib = _lib.load()
+            with torch.cuda.device(self.device):
+                _lib.check(lib.tq_symmetrize(_lib.ptr(self.H), self.columns, self.columns, _lib.stream()),
+                           "tq_symmetrize")
+            self._upper_only = False
+        return self.H
+
+    def damped_inverse(self, percdamp: float):
+        """gptq.py:94-106: (Hd, Hinv, info) with Hd = H/nsamples + percdamp*mean(diag)*I and
+        Hinv = cholesky_inverse(cholesky(Hd)); ``info`` is a device int (0 = ok)."""
+        key = float(percdamp)
+        if key in self._cache:
+            return self._cache[key]
+        if self.nsamples <= 0:
+            raise RuntimeError("quantize() called before add_batch(): the Hessian is empty")
+        lib = _lib.load()
+        m = self.columns
+        dev = self.device
+        Hd = torch.empty((m, m), dtype=torch.float32, device=dev)
+        Hinv = torch.empty((m, m), dtype=torch.float32, device=dev)
+        work = torch.empty(lib.tq_chol_workspace_floats(m), dtype=torch.float32, device=dev)
+        scratch = torch.empty(8, dtype=torch.float32, device=dev)
+        info = torch.zeros(1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            st = _lib.stream()
+            _lib.check(lib.tq_hessian_finalize(_lib.ptr(Hd), _lib.ptr(self.H), m, float(self.nsamples), key,
+                                               _lib.ptr(scratch), st), "tq_hessian_finalize")
+            _lib.check(lib.tq_chol_inverse(_lib.ptr(Hinv), _lib.ptr(Hd), m, _lib.ptr(work), _lib.ptr(info), st),
+                       "tq_chol_inverse")
+        for t in (work, scratch):
+            t.record_stream(torch.cuda.current_stream(dev))
+        self._cache[key] = (Hd, Hinv, info)
+        return self._cache[key]
+
+
+class GPTQ:
+    """gptq.py:21-230."""
+
+    def __init__(self, layer: nn.Linear, block_size: int = 128, percdamp: float = 0.01,
+                 hessian: Optional[HessianState] = None):
+        self.layer = layer
+        self.block_size = block_size
+        self.percdamp = percdamp
+        self.device = layer.weight.device
+        self.dtype = layer.weight.dtype
+        _lib.require_cuda(layer.weight, "layer.weight")
+        self.rows, self.columns = layer.weight.shape
+        if not (1 <= block_size <= 512):
+            raise ValueError("block_size must be in [1, 512]")
+        self.state = hessian if hessian is not None else HessianState(self.columns, self.device)
+        if self.state.columns != self.columns:
+            raise ValueError("shared HessianState has a different width than this layer's in_features")
+        self.alpha = None
+        self.mu = None
+        self.T = None
+        self.perm = None
+        self.T_int8 = None
+        self.info = None
+
+    # the reference exposes H and nsamples as plain attributes (gptq.py:50-51)
+    @property
+    def H(self) -> torch.Tensor:
+        return self.state.full()
+
+    @H.setter
+    def H(self, value: torch.Tensor):
+        self.state.H = value.to(device=self.device, dtype=torch.float32).contiguous()
+        self.state._upper_only = False
+        self.state._cache.clear()
+
+    @property
+    def nsamples(self) -> int:
+        return self.state.nsamples
+
+    @nsamples.setter
+    def nsamples(self, value: int):
+        self.state.nsamples = value
+        self.state._cache.clear()
+
+    def add_batch(self, inp: torch.Tensor):
+        """gptq.py:59-76: H += X'X over (batch, seq, in) or (tokens, in) activations."""
+        self.state.add_batch(inp)
+
+    @torch.no_grad()
+    def quantize(self, use_ssr: bool = True, aga: str = "hessian", order: Optional[str] = None,
+                 max_iter: int = 100) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+        """gptq.py:78-199.  New optional arguments keep the reference's behaviour by default:
+        aga   'hessian' (gptq.py:147-150) | 'activations' (main.py:177-180) | 'none'
+        order None -> 'ssr' if use_ssr else 'sequential'; 'actorder' = descending diag(H) (extension)."""
+        lib = _lib.load()
+        if aga not in _AGA:
+            raise ValueError(f"aga must be one of {sorted(_AGA)}")
+        if order is None:
+            order = "ssr" if use_ssr else "sequential"
+        if order not in ("ssr", "sequential", "actorder"):
+            raise ValueError("order must be 'ssr', 'sequential' or 'actorder'")
+        n, m, b = self.rows, self.columns, self.block_size
+        dev = self.device
+        nb = (m + b - 1) // b
+
+        Hd, Hinv, info = self.state.damped_inverse(self.percdamp)
+        static_perm = None
+        order_code = {"ssr": _lib.ORDER_SSR, "sequential": _lib.ORDER_SEQUENTIAL, "actorder": _lib.ORDER_STATIC}[order]
+        if order == "actorder":
+            static_perm = torch.argsort(torch.diagonal(Hd), descending=True, stable=True).to(torch.int32).contiguous()
+
+        def run(hinv):
+            W = self.layer.weight.data.detach().to(torch.float32).clone().contiguous()     # gptq.py:91
+            T8 = torch.empty((n, m), dtype=torch.int8, device=dev)
+            alpha = torch.empty((n, nb), dtype=torch.float32, device=dev)
+            mu = torch.empty((n, nb), dtype=torch.float32, device=dev)
+            perm = torch.empty(m, dtype=torch.int32, device=dev)
+            ws_bytes = lib.tq_sweep_workspace_bytes(n, m, b)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.tq_sweep_layer(_lib.ptr(W), W.stride(0), n, m, _lib.ptr(Hd), _lib.ptr(self.state.H),
+                                              _lib.ptr(hinv), b, order_code, _AGA[aga], int(max_iter),
+                                              _lib.ptr(static_perm), _lib.ptr(T8), _lib.ptr(alpha), _lib.ptr(mu),
+                                              _lib.ptr(perm), _lib.ptr(ws), ws_bytes, _lib.stream()),
+                           "tq_sweep_layer")
+            for t in (W, ws):
+                t.record_stream(torch.cuda.current_stream(dev))
+            return alpha, mu, T8, perm
+
+        if aga == "activations":
+            self.state.full()            # the AGA Gram reads H[blk, blk] on both sides of the diagonal
+        alpha, mu, T8, perm = run(Hinv)
+        self.info = int(info.item())     # the one host sync of the layer
+        if self.info != 0:
+            # gptq.py:104-106: Cholesky failed -> pseudo-inverse (library SVD, as in the reference), redo the sweep
+            Hinv = torch.linalg.pinv(Hd)
+            self.state._cache[float(self.percdamp)] = (Hd, Hinv, torch.zeros_like(info))
+            alpha, mu, T8, perm = run(Hinv)
+
+        self.alpha = alpha.to(self.dtype)
+        self.mu = mu.to(self.dtype)
+        self.T_int8 = T8
+        self.T = T8.to(self.dtype)                     # gptq.py:109: T has W's dtype
+        self.perm = perm.to(torch.int64)               # gptq.py:191
+        return self.alpha, self.mu, self.T, self.perm
+
+    fasterquant = quantize
+
+    def get_quantized_weight(self) -> torch.Tensor:
+        """gptq.py:201-230."""
+        if self.T is None:
+            raise RuntimeError("Must call quantize() first")
+        lib = _lib.load()
+        n, m, b = self.rows, self.columns, self.block_size
+        nb = (m + b - 1) // b
+        Wq = torch.empty((n, m), dtype=torch.float32, device=self.device)
+        alpha = self.alpha.float().contiguous()
+        mu = self.mu.float().contiguous()
+        perm = self.perm.to(torch.int32).contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.tq_dequant(_lib.ptr(alpha), _lib.ptr(mu), nb, _lib.ptr(self.T_int8), n, m, _lib.ptr(perm), b,
+                                      _lib.ptr(Wq), _lib.stream()), "tq_dequant")
+        return Wq.to(self.dtype)
+
+    def packed_codes(self):
+        """2-bit codes of T in original column positions (utils.pack_ternary layout) + per-block scales."""
+        try:
+            from .utils import pack_ternary
+        except ImportError:
+            from utils import pack_ternary
+        if self.T_int8 is None:
+            raise RuntimeError("Must call quantize() first")
+        packed, shape = pack_ternary(self.T_int8)
+        return {"packed": packed, "shape": tuple(shape), "alpha": self.alpha, "mu": self.mu, "perm": self.perm}
+
+
+class GPTQQuantizer:
+    """gptq.py:233-272."""
+
+    def __init__(self, model: nn.Module, block_size: int = 128, percdamp: float = 0.01, use_ssr: bool = True):
+        self.model = model
+        self.block_size = block_size
+        self.percdamp = percdamp
+        self.use_ssr = use_ssr
+        self.quantizers: Dict[str, GPTQ] = {}
+        self.calibration_data = []
+
+    def add_calibration_data(self, data: torch.Tensor):
+        self.calibration_data.append(data)
+
+    def prepare_quantizer(self, name: str, layer: nn.Linear):
+        self.quantizers[name] = GPTQ(layer, self.block_size, self.percdamp)
+
+    def quantize_layer(self, name: str) -> Dict[str, torch.Tensor]:
+        if name not in self.quantizers:
+            raise ValueError(f"Layer {name} not prepared for quantization")
+        alpha, mu, T, perm = self.quantizers[name].quantize(use_ssr=self.use_ssr)
+        return {"alpha": alpha, "mu": mu, "T": T, "perm": perm}
+
+
+@torch.no_grad()
+def quantize_layer(layer: nn.Linear, layer_name: str, calibration_activations: torch.Tensor,
+                   block_size: int = 128, percdamp: float = 0.01, use_ssr: bool = True,
+                   device=None) -> Dict[str, torch.Tensor]:
+    """Drop-in body for ``PT2LLMQuantizer.quantize_layer`` (main.py:102-230): same inputs, same CPU
+    dict {'alpha','mu','T' (int8),'perm'}; AGA is fed the raw-activation Gram (main.py:177-180)."""
+    dev = torch.device(device) if device is not None else layer.weight.device
+    if layer.weight.device != dev:
+        layer = layer.to(dev)
+    g = GPTQ(layer, block_size=block_size, percdamp=percdamp)
+    g.add_batch(calibration_activations.to(dev))
+    alpha, mu, _, perm = g.quantize(use_ssr=use_ssr, aga="activations")
+    return {"alpha": alpha.float().cpu(), "mu": mu.float().cpu(), "T": g.T_int8.cpu(), "perm": perm.cpu()}

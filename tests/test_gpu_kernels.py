@@ -1,0 +1,322 @@
+"""Stage-level parity: every CUDA kernel, called through the C ABI, against the numpy oracle and the
+committed golden fixtures (outputs of the unmodified reference).  Needs a B200: -m gpu."""
+
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+import parity
+import synth
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpu_util
+    return gpu_util
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+# ------------------------------------------------------------------ quantizer API vs reference outputs
+def test_atq_api_vs_reference_stages(G, golden_dir):
+    import tq100
+    g = _load(golden_dir, "atq_stages.npz")
+    W, X = G.dev(g["W"]), G.dev(g["X"])
+    q = tq100.AsymmetricTernaryQuantizer(max_iter=100)
+    a0, u0, T0 = q.ternary_init(W)
+    assert a0.shape == (64, 1) and T0.shape == (64, 128) and T0.dtype == torch.float32
+    assert np.array_equal(T0.cpu().numpy().astype(np.int8), g["init_T"])
+    np.testing.assert_allclose(a0.cpu().numpy(), g["init_alpha"], rtol=1e-5)
+    np.testing.assert_allclose(u0.cpu().numpy(), g["init_mu"], rtol=1e-4, atol=1e-9)
+    ag, ug = q.build_optimal_grid(W, G.dev(g["init_T"].astype(np.float32)))
+    np.testing.assert_allclose(ag.cpu().numpy(), g["grid_alpha"], rtol=1e-5)
+    np.testing.assert_allclose(ug.cpu().numpy(), g["grid_mu"], rtol=1e-4, atol=1e-8)
+    Tr = q.flexible_round(W, G.dev(g["grid_alpha"]), G.dev(g["grid_mu"]))
+    assert np.array_equal(Tr.cpu().numpy().astype(np.int8), g["round_T"])
+    a1, u1, T1 = q.iterative_ternary_fitting(W, G.dev(g["init_alpha"]), G.dev(g["init_mu"]),
+                                             G.dev(g["init_T"].astype(np.float32)))
+    assert np.array_equal(T1.cpu().numpy().astype(np.int8), g["itf_T"])
+    np.testing.assert_allclose(a1.cpu().numpy(), g["itf_alpha"], rtol=1e-5)
+    a2, u2 = q.activation_aware_grid_alignment(W, G.dev(g["itf_T"].astype(np.float32)), X)
+    np.testing.assert_allclose(a2.cpu().numpy(), g["aga_alpha"], rtol=1e-4)
+    np.testing.assert_allclose(u2.cpu().numpy(), g["aga_mu"], rtol=1e-3, atol=1e-7)
+    aq, uq, Tq = q.quantize(W, X)
+    assert np.array_equal(Tq.cpu().numpy().astype(np.int8), g["q_T"])
+    np.testing.assert_allclose(aq.cpu().numpy(), g["q_alpha"], rtol=1e-4)
+    np.testing.assert_allclose(uq.cpu().numpy(), g["q_mu"], rtol=1e-3, atol=1e-7)
+    an, un, Tn = q.quantize(W, None)
+    assert np.array_equal(Tn.cpu().numpy().astype(np.int8), g["qn_T"])
+    np.testing.assert_allclose(an.cpu().numpy(), g["qn_alpha"], rtol=1e-5)
+    Wc = q.dequantize(an, un, Tn)
+    assert abs(tq100.compute_quantization_error(W, Wc) -
+               oracle.compute_quantization_error(g["W"], oracle.dequantize(g["qn_alpha"], g["qn_mu"], g["qn_T"]))) < 1e-6
+
+
+def test_atq_degenerate_rows(G, golden_dir):
+    """constant / zero / two-valued rows among normal rows behave as in the reference's
+    global loop (a zero-init row is not stopped at iteration 0)."""
+    import tq100
+    g = _load(golden_dir, "atq_degenerate.npz")
+    a, u, T = tq100.AsymmetricTernaryQuantizer().quantize(G.dev(g["W"]), None)
+    T = T.cpu().numpy().astype(np.int8)
+    assert parity.code_agreement(T, g["T"]) >= 0.999
+    same = (T == g["T"]).all(axis=1)
+    for r in (3, 7, 11):
+        assert same[r], f"degenerate row {r} differs from the reference"
+    np.testing.assert_allclose(a.cpu().numpy()[same], g["alpha"][same], rtol=1e-4, atol=1e-9)
+
+
+@pytest.mark.parametrize("b", [8, 40, 64, 72, 200, 256])
+def test_atq_other_block_widths(G, golden_dir, b):
+    import tq100
+    g = _load(golden_dir, "atq_widths.npz")
+    a, u, T = tq100.AsymmetricTernaryQuantizer().quantize(G.dev(g[f"W{b}"]), G.dev(g[f"X{b}"][None]))
+    assert np.array_equal(T.cpu().numpy().astype(np.int8), g[f"T{b}"])
+    np.testing.assert_allclose(a.cpu().numpy(), g[f"alpha{b}"], rtol=1e-4)
+    np.testing.assert_allclose(u.cpu().numpy(), g[f"mu{b}"], rtol=1e-3, atol=1e-7)
+
+
+@pytest.mark.parametrize("gather", [False, True])
+@pytest.mark.parametrize("dist", ["normal", "student_t"])
+def test_atq_block_kernel_vs_oracle(G, gather, dist):
+    """The fused sweep kernel (init + ITF + AGA + error) on 4096 rows, contiguous and gathered columns."""
+    from tq100 import _lib
+    rng = np.random.default_rng(5)
+    n, m, b = 4096, 1024, 128
+    if dist == "normal":
+        W = synth.make_weight(n, m, seed=21, row_offset=0.004)
+    else:
+        W = (rng.standard_t(3, size=(n, m)) * 0.02).astype(np.float32)
+    Xh = rng.standard_normal((512, m)).astype(np.float32)
+    Hd, _ = oracle.damped_inverse(Xh.T @ Xh, 512)
+    blk = np.sort(rng.choice(m, b, replace=False)) if gather else np.arange(256, 256 + b)
+    if gather:
+        rng.shuffle(blk)
+    ra, ru, rT = oracle.atq_quantize(W[:, blk], X=Hd[np.ix_(blk, blk)])
+    rE = W[:, blk] - (ra * rT + ru)
+    Wd, Hdd = G.dev(W), G.dev(Hd)
+    idx = G.i32(blk) if gather else None
+    s1d = G.aga_vector(Hdd, idx, 256, b, _lib.AGA_HESSIAN)
+    a, u, T, E, iters = G.atq_block(Wd, blk_idx=idx, col0=256, b=b, s1d=s1d)
+    agree = parity.code_agreement(T, rT)
+    assert agree >= 0.9999, agree
+    same = (T == rT.astype(np.int8)).all(axis=1)
+    assert same.mean() > 0.995
+    assert parity.scale_rel_err(a, ra, same[:, None]) <= parity.SCALE_RTOL
+    assert parity.scale_rel_err(u, ru, same[:, None], floor=np.abs(ra)) <= parity.SCALE_RTOL
+    np.testing.assert_allclose(E[same], rE[same], rtol=0, atol=2e-6)
+    # per-row early exit does far fewer rounds than the reference's global loop
+    _, _, _, g_iters = oracle.iterative_ternary_fitting(W[:, blk], *oracle.ternary_init(W[:, blk]), return_iters=True)
+    assert iters.max() <= g_iters and iters.mean() < g_iters
+
+
+# ------------------------------------------------------------------ SSR
+def test_ssr_vs_reference_fixture(G, golden_dir):
+    import tq100
+    g = _load(golden_dir, "ssr_select.npz")
+    W = G.dev(g["W"])
+    rem = torch.from_numpy(g["remaining"]).to("cuda:0")
+    sim = tq100.compute_column_similarity_to_mean(W, rem)
+    np.testing.assert_allclose(sim.cpu().numpy(), g["sim"], rtol=1e-4, atol=1e-6)
+    blk, new_rem = tq100.select_next_block_ssr(W, rem, 128)
+    assert blk.dtype == torch.int64
+    assert np.array_equal(blk.cpu().numpy(), g["block"])
+    assert np.array_equal(new_rem.cpu().numpy(), g["new_remaining"])
+    small = torch.from_numpy(g["small"]).to("cuda:0")
+    blk2, rem2 = tq100.select_next_block_ssr(W, small, 128)
+    assert np.array_equal(blk2.cpu().numpy(), g["block_small"]) and rem2.numel() == 0
+
+
+@pytest.mark.parametrize("n,m,rem_n", [(512, 4096, 4096), (1000, 11008, 7000), (33, 300, 129)])
+def test_ssr_select_vs_oracle(G, n, m, rem_n):
+    import tq100
+    rng = np.random.default_rng(n + m)
+    W = synth.make_weight(n, m, seed=31, row_offset=0.01)
+    W[:, rng.choice(m, m // 8, replace=False)] *= 3.0
+    rem = np.sort(rng.choice(m, rem_n, replace=False)).astype(np.int64)
+    rb, rr = oracle.select_next_block_ssr(W, rem, 128)
+    blk, new_rem = tq100.select_next_block_ssr(G.dev(W), torch.from_numpy(rem).to("cuda:0"), 128)
+    blk, new_rem = blk.cpu().numpy(), new_rem.cpu().numpy()
+    assert len(set(blk.tolist())) == 128 and np.array_equal(np.sort(np.concatenate([blk, new_rem])), rem)
+    assert np.array_equal(new_rem, np.sort(new_rem))
+    # membership may differ only at the top-k boundary where similarities tie to fp32 rounding
+    sim64 = oracle.column_similarity_to_mean(W.astype(np.float64), rem)
+    pos = {c: i for i, c in enumerate(rem.tolist())}
+    kth = np.sort(sim64)[-128]
+    for c in set(blk.tolist()) ^ set(rb.tolist()):
+        assert abs(sim64[pos[c]] - kth) < 5e-6, "block membership differs away from the top-k boundary"
+    if set(blk.tolist()) == set(rb.tolist()):
+        s = sim64[[pos[c] for c in blk.tolist()]]
+        assert (np.diff(s) <= 5e-6).all(), "block is not in descending-similarity order"
+
+
+def test_ssr_ties_go_to_lower_position(G):
+    import tq100
+    W = np.tile(np.linspace(-1, 1, 16, dtype=np.float32)[:, None], (1, 200))   # all columns identical
+    blk, rem = tq100.select_next_block_ssr(G.dev(W), torch.arange(200, device="cuda:0"), 128)
+    assert np.array_equal(blk.cpu().numpy(), np.arange(128))
+    assert np.array_equal(rem.cpu().numpy(), np.arange(128, 200))
+
+
+# ------------------------------------------------------------------ Hessian
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("nt,m", [(700, 320), (2048, 768), (130, 97)])
+def test_hessian_ffma_vs_fp64(G, dtype, nt, m):
+    from tq100 import _lib
+    rng = np.random.default_rng(nt + m)
+    X = torch.from_numpy(rng.standard_normal((nt, m)).astype(np.float32)).to(dtype).to("cuda:0")
+    H = G.hessian(X, m, _lib.HESS_FFMA).cpu().numpy()
+    Xd = X.double().cpu().numpy()
+    ref = Xd.T @ Xd
+    np.testing.assert_allclose(H, ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
+    assert np.array_equal(H, H.T)
+    # accumulation (H += ...) over two calls
+    H2 = G.hessian(X, m, _lib.HESS_FFMA, H=torch.from_numpy(H).to("cuda:0")).cpu().numpy()
+    np.testing.assert_allclose(H2, 2 * ref, rtol=1e-5, atol=2e-5 * np.abs(ref).max())
+
+
+_TC_SCRIPT = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, {root!r}); sys.path.insert(0, {root!r} + "/tests")
+import gpu_util as G
+from tq100 import _lib
+dtype = {{"f16": torch.float16, "bf16": torch.bfloat16}}[{dtype!r}]
+nt, m, calls = {nt}, {m}, {calls}
+rng = np.random.default_rng(nt + m)
+H = None
+ref = np.zeros((m, m))
+for c in range(calls):
+    X = torch.from_numpy(rng.standard_normal((nt, m)).astype(np.float32)).to(dtype).to("cuda:0")
+    H = G.hessian(X, m, _lib.HESS_TCGEN05, H=H)
+    Xd = X.double().cpu().numpy(); ref += Xd.T @ Xd
+torch.cuda.synchronize()
+H = H.cpu().numpy()
+err = np.abs(H - ref).max() / np.abs(ref).max()
+print("relerr", err)
+assert np.array_equal(H, H.T)
+assert err < 1e-5, err
+print("TC_OK")
+"""
+
+
+@pytest.mark.parametrize("dtype", ["f16", "bf16"])
+@pytest.mark.parametrize("nt,m,calls", [(64, 256, 1), (2048, 768, 2), (1000, 320, 1), (5000, 4096, 1), (333, 1096, 3)])
+def test_hessian_tcgen05_vs_fp64(dtype, nt, m, calls):
+    """tcgen05/TMEM/TMA SYRK vs fp64: fp16/bf16 products are exact, so only fp32 accumulation order
+    differs.  Run in a child process under a timeout so a wedged pipeline cannot hang the suite."""
+    code = _TC_SCRIPT.format(root=ROOT, dtype=dtype, nt=nt, m=m, calls=calls)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=180)
+    assert p.returncode == 0 and "TC_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+def test_hessian_auto_path_and_api(G):
+    """GPTQ.add_batch: fp16 activations (3-D and 2-D) through the tcgen05 path == fp32 activations through FFMA."""
+    import tq100
+    m = 512
+    X = synth.make_activations(3, 200, m, seed=77)
+    layer = torch.nn.Linear(m, 64, bias=False).to("cuda:0")
+    g16, g32 = tq100.GPTQ(layer), tq100.GPTQ(layer)
+    for i in range(3):
+        xi = torch.from_numpy(X[i]).to("cuda:0")
+        g16.add_batch(xi[None] if i % 2 == 0 else xi)
+        g32.add_batch(xi.float())
+    assert g16.nsamples == g32.nsamples == 600
+    Xf = X.astype(np.float64).reshape(-1, m)
+    ref = Xf.T @ Xf
+    for g in (g16, g32):
+        H = g.H.cpu().numpy()
+        np.testing.assert_allclose(H, ref, rtol=1e-5, atol=1e-5 * np.abs(ref).max())
+        assert np.array_equal(H, H.T)
+
+
+# ------------------------------------------------------------------ damped Cholesky inverse
+@pytest.mark.parametrize("m,lam", [(128, 0.5), (320, 0.5), (1000, 1.0), (2048, 0.5)])
+def test_damped_inverse_vs_oracle(G, m, lam):
+    X = synth.make_activations(4, max(256, m // 2), m, seed=41, lam=lam).astype(np.float32).reshape(-1, m)
+    Hraw = (X.T @ X).astype(np.float32)
+    Hd_o, Hinv_o = oracle.damped_inverse(Hraw.copy(), X.shape[0], 0.01)
+    Hd, Hinv, info = G.finalize_and_invert(G.dev(Hraw), X.shape[0], 0.01)
+    assert info == 0
+    Hd, Hinv = Hd.cpu().numpy(), Hinv.cpu().numpy()
+    np.testing.assert_allclose(Hd, Hd_o, rtol=2e-6, atol=1e-7 * np.abs(Hd_o).max())
+    assert np.array_equal(Hinv, Hinv.T)
+    I = np.eye(m)
+    res = np.abs(Hd.astype(np.float64) @ Hinv.astype(np.float64) - I).max()
+    res_o = np.abs(Hd_o.astype(np.float64) @ Hinv_o.astype(np.float64) - I).max()
+    assert res <= max(10 * res_o, 5e-5), (res, res_o)
+    exact = np.linalg.inv(Hd_o.astype(np.float64))
+    e = np.abs(Hinv - exact).max() / np.abs(exact).max()
+    e_o = np.abs(Hinv_o - exact).max() / np.abs(exact).max()
+    assert e <= max(10 * e_o, 1e-5), (e, e_o)
+
+
+def test_cholesky_reports_non_positive_definite(G):
+    H = np.eye(300, dtype=np.float32)
+    H[200, 200] = -1.0
+    _, _, info = G.finalize_and_invert(G.dev(H * 300), 300, 0.0)
+    assert info == 201
+
+
+# ------------------------------------------------------------------ error feedback
+@pytest.mark.parametrize("gather", [False, True])
+def test_err_feedback_vs_numpy(G, gather):
+    rng = np.random.default_rng(9)
+    n, m, b = 300, 1000, 128
+    W = synth.make_weight(n, m, seed=51)
+    E = (rng.standard_normal((n, b)) * 0.01).astype(np.float32)
+    A = rng.standard_normal((m, m)).astype(np.float32)
+    Hinv = (A @ A.T / m + np.eye(m, dtype=np.float32)).astype(np.float32)
+    if gather:
+        perm = rng.permutation(m)
+        blk, rem = perm[:b], np.sort(perm[b:b + 700])
+    else:
+        blk, rem = np.arange(128, 256), np.arange(256, m)
+    C = Hinv[np.ix_(blk, rem)] / np.maximum(np.diag(Hinv)[blk], 1e-8)[:, None]
+    ref = W.copy()
+    ref[:, rem] -= E @ C
+    Wd = G.err_feedback(G.dev(W), G.dev(E), G.dev(Hinv), G.i32(blk) if gather else None, 128, b,
+                        G.i32(rem) if gather else None, 256, len(rem)).cpu().numpy()
+    np.testing.assert_allclose(Wd, ref, rtol=0, atol=2e-7)
+    untouched = np.setdiff1d(np.arange(m), rem)
+    assert np.array_equal(Wd[:, untouched], W[:, untouched])
+
+
+# ------------------------------------------------------------------ codec (bit exact)
+def test_pack_unpack_vs_reference_fixture(G, golden_dir):
+    import tq100
+    g = _load(golden_dir, "pack.npz")
+    i = 0
+    while f"T{i}" in g.files:
+        for src in (G.dev(g[f"T{i}"]), G.dev(g[f"T{i}"].astype(np.float32))):
+            packed, shape = tq100.pack_ternary(src)
+            assert packed.dtype == torch.uint8 and tuple(shape) == g[f"T{i}"].shape
+            assert np.array_equal(packed.cpu().numpy(), g[f"packed{i}"])
+            un = tq100.unpack_ternary(packed, shape)
+            assert un.dtype == torch.int8 and np.array_equal(un.cpu().numpy(), g[f"unpacked{i}"])
+        i += 1
+
+
+@pytest.mark.parametrize("count", [1, 3, 16, 17, 4096 * 4096 + 5])
+def test_pack_roundtrip_and_oracle(G, count):
+    import tq100
+    rng = np.random.default_rng(count % 1000)
+    T = rng.integers(-1, 2, size=count).astype(np.int8)
+    packed, shape = tq100.pack_ternary(G.dev(T))
+    if count < 1 << 20:
+        assert np.array_equal(packed.cpu().numpy(), oracle.pack_ternary(T)[0])
+    else:   # full 4096 x 4096 layer: checksum of the oracle's bytes + round trip
+        ref = oracle.pack_ternary(T)[0]
+        assert int(packed.cpu().numpy().astype(np.uint64).sum()) == int(ref.astype(np.uint64).sum())
+        assert np.array_equal(packed.cpu().numpy()[::4099], ref[::4099])
+    assert np.array_equal(tq100.unpack_ternary(packed, shape).cpu().numpy(), T)
