@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""Headline benchmark: LLaMA-2-7B-shaped ternary GPTQ (PT2-LLM) wall-time on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over the whole LLaMA-2-7B-shaped model: for each of the 32
+transformer layers and each of its 7 linears, GPTQ.add_batch (Hessian over 128 x 2048 calibration
+tokens) + GPTQ.quantize (damped Cholesky inverse, SSR column sweep with ITF/AGA grid fit and error
+feedback) -- BASELINE.json configs[1].  Synthetic data: random-init weights N(0, 0.02^2) per linear;
+one layer's four distinct calibration inputs (attention in, o_proj in, MLP in, down_proj in: 12.2 GB
+fp16, far larger than L2) are reused for the 32 layers because 32 x 12.2 GB does not fit in HBM.
+
+Prints ONE JSON line (see the keys at the bottom).  `value` times the device-resident path with CUDA
+events; `e2e` drives the same public API from pinned HOST buffers (weights and activations copied
+host->device, results copied device->host, every step, inside the timed region).
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LLAMA2_7B = dict(name="llama-2-7b", d=4096, ffn=11008, layers=32)
+SAMPLES, SEQ = 128, 2048
+# (linear name, out_features n, in_features m, which of the layer's inputs it reads)
+def linears(cfg):
+    d, f = cfg["d"], cfg["ffn"]
+    return [("q_proj", d, d, "attn_in"), ("k_proj", d, d, "attn_in"), ("v_proj", d, d, "attn_in"),
+            ("o_proj", d, d, "o_in"), ("gate_proj", f, d, "mlp_in"), ("up_proj", f, d, "mlp_in"),
+            ("down_proj", d, f, "down_in")]
+
+
+def hessian_useful_flops(nt, m):
+    return nt * m * (m + 1)          # SYRK, upper triangle; dense-equivalent is 2*nt*m*m
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx = float(parts[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        # median over the samples taken under load (above 60 % of the peak sample filters idle gaps)
+        loaded = [x for x in sm if sm and x >= 0.6 * sm[-1]]
+        med = loaded[len(loaded) // 2] if loaded else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU arm
+def cpu_arm(threads=None, hess_tokens=16384):
+    """The reference's CPU implementation of the path on the host cores.  The reference is pure
+    Python/PyTorch and cannot travel to the GPU box, so this is the oracle's torch-CPU port
+    (oracle/torch_port.py: same library, oneMKL + LAPACK, all threads), on a bounded sample: ONE
+    4096x4096 linear -- Hessian over `hess_tokens` of the 262144 tokens (cost is exactly linear in
+    tokens, gptq.py:75) + the damped inverse + the full SSR sweep -- extrapolated to the model by
+    stage: Hessian by 2*Nt*m^2, inverse by m^3, sweep by n*m^2."""
+    import torch
+    from oracle import torch_port
+    cores = threads or os.cpu_count()
+    torch.set_num_threads(cores)
+    n = m = 4096
+    g = torch.Generator().manual_seed(1)
+    W = torch.randn((n, m), generator=g) * 0.02
+    Bm = torch.randn((64, m), generator=g)
+    X = torch.randn((hess_tokens, m), generator=g) + (0.5 / 8.0) * (torch.randn((hess_tokens, 64), generator=g) @ Bm)
+    X = X.half().float()
+    t0 = time.perf_counter()
+    H = torch.zeros((m, m))
+    ns = 0
+    for i in range(0, hess_tokens, SEQ):
+        ns += torch_port.hessian_add(H, X[i:i + SEQ])
+    t_h = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    torch_port.damped_inverse(H, ns, 0.01)
+    t_inv = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    torch_port.quantize_layer(W, H, ns, 128, 0.01, use_ssr=True, aga="hessian")
+    t_q = time.perf_counter() - t0            # includes one more damped inverse
+    t_sweep = max(t_q - t_inv, 1e-9)
+    cfg = LLAMA2_7B
+    tot_h = tot_inv = tot_sw = 0.0
+    for _, nn_, mm_, _ in linears(cfg):
+        tot_h += t_h * (SAMPLES * SEQ / hess_tokens) * (mm_ / m) ** 2
+        tot_inv += t_inv * (mm_ / m) ** 3
+        tot_sw += t_sweep * (nn_ / n) * (mm_ / m) ** 2
+    total = cfg["layers"] * (tot_h + tot_inv + tot_sw)
+    return {"value": total, "unit": "s", "cores": cores, "kind": "port",
+            "sample": (f"oracle/torch_port.py (torch CPU fp32, {cores} threads), one 4096x4096 linear: Hessian over "
+                       f"{hess_tokens} of {SAMPLES * SEQ} tokens ({t_h:.2f} s), damped inverse ({t_inv:.2f} s), "
+                       f"full SSR sweep ({t_sweep:.2f} s); extrapolated to 32 layers x 7 linears "
+                       f"(Hessian ~ 2*Nt*m^2, inverse ~ m^3, sweep ~ n*m^2)"),
+            "measured_s": t_h + t_inv + t_q}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    for _ in range(args.warmup):
+        pass                                   # BLAS needs no warm-up beyond the first call inside the sample
+    vals = []
+    for _ in range(max(1, args.steps)):
+        vals.append(cpu_arm())
+    best = min(vals, key=lambda r: r["value"])
+    v = sum(r["value"] for r in vals) / len(vals)
+    line = {"impl": "reference", "metric": "LLaMA-2-7B ternary PTQ wall-time", "value": v, "unit": "s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": v * 1e3,
+            "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, reference=True),
+            "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    line["cpu_baseline"]["value"] = v
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, reference=False):
+    return {"workload": "LLaMA-2-7B-shaped ternary GPTQ with SSR column reordering "
+                        "(32 layers x {q,k,v,o 4096x4096; gate,up 11008x4096; down 4096x11008}, "
+                        "128x2048 calibration tokens per linear, block 128, percdamp 0.01, ITF + AGA(hessian))",
+            "baseline_config": "configs[1]", "order": "ssr", "aga": "hessian", "block_size": 128,
+            "activations": "fp16, one layer's 4 distinct inputs (12.2 GB) reused for all 32 layers",
+            "cache": "inputs (12.2 GB activations + 25.9 GB weights) far exceed the 126 MB L2; no explicit flush",
+            "hessians_per_layer": 7, "parallelism": "1 GPU" if args.gpus == 1 else f"{args.gpus} GPUs: "
+            "Hessian sample-sharded + NCCL allreduce, sweep row-sharded, H^-1 replicated"}
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--layers", type=int, default=LLAMA2_7B["layers"], help="(debug) fewer layers; the line says so")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import tq100
+    from tq100 import _lib
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from tq100 import sharded as par
+    from tq100.pipeline import HostPipeline, LinearView
+    ctx = par.ShardContext(rank, world, dev)
+
+    cfg = dict(LLAMA2_7B, layers=args.layers)
+    lins = linears(cfg)
+    nt = SAMPLES * SEQ
+
+    # ---- synthetic inputs, resident in HBM before the timed region -----------------------------
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    lam, r = 0.5, 64
+    acts = {}
+    my_samples = ctx.my_samples(SAMPLES)                       # calibration samples of this rank
+    for key, width in (("attn_in", cfg["d"]), ("o_in", cfg["d"]), ("mlp_in", cfg["d"]), ("down_in", cfg["ffn"])):
+        B = torch.randn((r, width), device=dev, generator=gen)
+        x = torch.empty((len(my_samples), SEQ, width), device=dev, dtype=torch.float16)
+        for j, s in enumerate(my_samples):
+            g2 = torch.Generator(device=dev).manual_seed(100000 + 1000 * (hash(key) % 97) + s)
+            z = torch.randn((SEQ, width), device=dev, generator=g2)
+            f = torch.randn((SEQ, r), device=dev, generator=g2)
+            x[j] = (z + (lam / r ** 0.5) * (f @ B)).to(torch.float16)
+        acts[key] = x
+    weights = []
+    for li in range(cfg["layers"]):
+        ws = {}
+        for name, n, m, _ in lins:
+            gw = torch.Generator(device=dev).manual_seed(7 * li + hash(name) % 1000)
+            ws[name] = torch.randn((n, m), device=dev, generator=gw) * 0.02
+        weights.append(ws)
+    torch.cuda.synchronize()
+
+    hess_events = []
+    results_keep = {}
+
+    def quantize_model(record=False):
+        for li in range(cfg["layers"]):
+            for name, n, m, src in lins:
+                layer = LinearView(weights[li][name])
+                g = par.ShardedGPTQ(layer, ctx, block_size=128, percdamp=0.01)
+                if record:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                g.add_batch(acts[src])
+                if record:
+                    e1.record()
+                    hess_events.append((e0, e1, acts[src].shape[0] * SEQ, m))
+                out = g.quantize(use_ssr=True)
+                results_keep["last"] = out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        quantize_model()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        quantize_model(record=True)
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = ms_per_step / 1e3
+
+    # roofline of the dominant kernel (hessian_tc_kernel), live CUDA-event timing per launch
+    flops = sum(hessian_useful_flops(t_, m_) for _, _, t_, m_ in hess_events)
+    h_ms = sum(a.elapsed_time(b) for a, b, _, _ in hess_events)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    achieved = flops / (h_ms * 1e-3) / 1e12 if h_ms > 0 else 0.0
+    roofline = {"kernel": "hessian_tc_kernel", "bound": "tensor", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+                               if peaks else "fallback 1.4 PFLOP/s sustained",
+                "flops_counted": "useful SYRK flops Nt*m*(m+1) per launch (dense-equivalent 2*Nt*m^2 is 2x)",
+                "share_of_step": h_ms / ms if ms > 0 else None, "launches": len(hess_events)}
+
+    # ---- e2e: same API from pinned host buffers, copies inside the timed region ------------------
+    e2e = None
+    if not args.no_e2e and world == 1:
+        # one layer's weights and the four calibration inputs in pinned host memory, streamed per layer
+        host_acts = {k: v.reshape(-1, v.shape[-1]).cpu().pin_memory() for k, v in acts.items()}
+        host_w = {name: weights[0][name].cpu().pin_memory() for name, _, _, _ in lins}
+        order = ["attn_in", "o_in", "mlp_in", "down_in"]
+        groups_one_layer = [(host_acts[k], [(name, host_w[name]) for name, _, _, src in lins if src == k])
+                            for k in order]
+        pipe = HostPipeline(dev, block_size=128, percdamp=0.01, use_ssr=True, aga="hessian")
+        pipe.run(groups_one_layer)                                 # warm-up (allocations, pinned outputs)
+        torch.cuda.synchronize()
+        pipe.h2d_bytes = pipe.d2h_bytes = 0
+        t0 = time.perf_counter()
+        for _ in range(cfg["layers"]):
+            res = pipe.run(groups_one_layer)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {"value": dt, "unit": "s", "h2d_bytes_per_step": int(pipe.h2d_bytes),
+               "d2h_bytes_per_step": int(pipe.d2h_bytes),
+               "note": "HostPipeline.run per layer: each of the layer's 4 distinct calibration inputs and 7 weights "
+                       "copied from pinned host memory on a side stream (double-buffered against compute), "
+                       "alpha/mu/T(int8)/perm copied back to pinned host memory; wall clock around all 32 layers"}
+        del host_acts, host_w, pipe, res
+    if rank == 0:
+        line = {"metric": "LLaMA-2-7B ternary PTQ wall-time", "value": value, "unit": "s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+                "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": workload_config(args), "clocks": clocks,
+                "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e}
+        if args.layers != LLAMA2_7B["layers"]:
+            line["config"]["workload"] += f" [DEBUG: only {args.layers} of 32 layers]"
+        line["dtype_note"] = "fp32 arithmetic; fp16 activations enter the tensor cores exactly, fp32 accumulate"
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_arm()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

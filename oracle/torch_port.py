@@ -1,0 +1,105 @@
+"""Oracle, timing variant: the same algorithm restated on torch CPU tensors so that every stage runs on
+all host cores through the library the reference itself uses (PyTorch CPU: oneMKL GEMM, LAPACK
+potrf/potri, multi-threaded elementwise kernels).  TEST / BASELINE INFRASTRUCTURE -- used only by
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` arm and by ``tests/`` (which pin it to the same
+golden fixtures as the numpy oracle).  Follows gptq.py:59-199, quantizer.py:32-277, reorder.py:36-143.
+"""
+
+import torch
+
+_TINY = 1e-8
+
+
+def _grid(W, T):
+    b = W.shape[1]
+    wt, ts, ws, t2 = (W * T).sum(1, True), T.sum(1, True), W.sum(1, True), (T * T).sum(1, True)
+    den = (b * t2 - ts * ts).clamp(min=_TINY)                       # quantizer.py:99-100
+    return (b * wt - ts * ws) / den, (t2 * ws - ts * wt) / den      # quantizer.py:103,106
+
+
+def _round(W, alpha, mu):
+    Z = (W - mu) / alpha.clamp(min=_TINY)                           # quantizer.py:125-126
+    return (Z > 0.5).to(W.dtype) - (Z < -0.5).to(W.dtype)           # quantizer.py:130-132
+
+
+def atq_block(W, gram_in=None, gram=None, max_iter=100):
+    """init (quantizer.py:49-67) -> ITF with the global stop test (:160-175) -> AGA (:207-246).
+    gram_in: matrix handed to AGA as 'X' (S = X'X); gram: S itself."""
+    mu = W.mean(1, keepdim=True)
+    Wc = W - mu
+    delta = 0.75 * Wc.abs().mean(1, keepdim=True)
+    T = (Wc > delta).to(W.dtype) - (Wc < -delta).to(W.dtype)
+    alpha = (T * Wc).sum(1, True) / T.abs().sum(1, True).clamp(min=_TINY)
+    T_prev = torch.zeros_like(T)
+    for _ in range(max_iter):
+        if torch.equal(T, T_prev):
+            break
+        T_prev = T
+        alpha, mu = _grid(W, T)
+        T = _round(W, alpha, mu)
+    S = gram if gram is not None else (gram_in.T @ gram_in if gram_in is not None else None)
+    if S is not None:
+        s1 = S.sum(1, keepdim=True)                                 # S @ 1
+        d = float(s1.sum())
+        v, ws1, wts1, t2s1 = T @ s1, W @ s1, (W * T) @ s1, (T * T) @ s1
+        den = (d * t2s1 - v * v).clamp(min=_TINY)
+        alpha, mu = (d * wts1 - v * ws1) / den, (t2s1 * ws1 - v * wts1) / den
+    return alpha, mu, T
+
+
+def ssr_select(W, remaining, block):
+    if remaining.numel() <= block:                                  # reorder.py:125-126
+        return remaining, remaining[:0]
+    Wr = W[:, remaining]
+    wm = Wr.mean(1, keepdim=True)
+    sim = ((Wr / Wr.norm(dim=0, keepdim=True).clamp(min=_TINY)).T @ (wm / wm.norm().clamp(min=_TINY))).squeeze(1)
+    top = torch.topk(sim, block).indices                            # reorder.py:133
+    keep = torch.ones(remaining.numel(), dtype=torch.bool)
+    keep[top] = False
+    return remaining[top], remaining[keep]
+
+
+def hessian_add(H, X):
+    X = X.reshape(-1, X.shape[-1]).to(H.dtype)                      # gptq.py:68-75
+    H += X.T @ X
+    return X.shape[0]
+
+
+def damped_inverse(Hraw, nsamples, percdamp=0.01):
+    H = Hraw / nsamples                                             # gptq.py:94-103
+    H.diagonal().add_(percdamp * torch.diag(H).mean())
+    return H, torch.cholesky_inverse(torch.linalg.cholesky(H))
+
+
+def quantize_layer(W, Hraw, nsamples, block=128, percdamp=0.01, use_ssr=True, aga="hessian", max_iter=100):
+    """gptq.py:78-199."""
+    W = W.clone()
+    n, m = W.shape
+    H, Hinv = damped_inverse(Hraw, nsamples, percdamp)
+    dinv = torch.diag(Hinv).clamp(min=_TINY)
+    T_full = torch.zeros_like(W)
+    alphas, mus, perm = [], [], []
+    remaining = torch.arange(m)
+    done = 0
+    while done < m:
+        if use_ssr:
+            blk, remaining = ssr_select(W, remaining, block)
+            rem = remaining
+        else:
+            blk, rem = torch.arange(done, min(done + block, m)), torch.arange(min(done + block, m), m)
+        perm.append(blk)
+        Wb = W[:, blk]
+        if aga == "hessian":
+            a, u, Tb = atq_block(Wb, gram_in=H[blk][:, blk], max_iter=max_iter)
+        elif aga == "activations":
+            a, u, Tb = atq_block(Wb, gram=Hraw[blk][:, blk], max_iter=max_iter)
+        else:
+            a, u, Tb = atq_block(Wb, max_iter=max_iter)
+        alphas.append(a)
+        mus.append(u)
+        T_full[:, blk] = Tb
+        if rem.numel() > 0:
+            E = Wb - (a * Tb + u)
+            W[:, rem] -= E @ (Hinv[blk][:, rem] / dinv[blk][:, None])   # gptq.py:173-186
+        done += blk.numel()
+    return torch.cat(alphas, 1), torch.cat(mus, 1), T_full, torch.cat(perm)

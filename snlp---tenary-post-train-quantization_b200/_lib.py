@@ -108,3 +108,9 @@ def dtype_code(dt):
     if dt == torch.bfloat16:
         return BF16
     raise RuntimeError(f"unsupported activation dtype {dt}: use float32, float16 or bfloat16")
+
+
+def comm_ready():
+    """True once the in-library NCCL communicator (row-sharded SSR statistics) is initialised."""
+    lib = load()
+    return hasattr(lib, "tq_comm_ready") and bool(lib.tq_comm_ready())

@@ -113,9 +113,20 @@ def test_atq_block_kernel_vs_oracle(G, gather, dist):
     assert agree >= 0.9999, agree
     same = (T == rT.astype(np.int8)).all(axis=1)
     assert same.mean() > 0.995
-    assert parity.scale_rel_err(a, ra, same[:, None]) <= parity.SCALE_RTOL
-    assert parity.scale_rel_err(u, ru, same[:, None], floor=np.abs(ra)) <= parity.SCALE_RTOL
-    np.testing.assert_allclose(E[same], rE[same], rtol=0, atol=2e-6)
+    # scales: 1e-4 relative, or -- on heavy-tailed rows where the grid's denominator cancels -- within the
+    # fp32 oracle's own distance from the fp64 oracle (the adjudication protocol of SURVEY 8c)
+    a64, u64, T64 = oracle.atq_quantize(W[:, blk].astype(np.float64), X=Hd[np.ix_(blk, blk)].astype(np.float64))
+    ok64 = (same & (rT == T64).all(axis=1))[:, None]
+    floor_a = parity.scale_rel_err(ra, a64, ok64)
+    floor_u = parity.scale_rel_err(ru, u64, ok64, floor=np.abs(a64))
+    assert parity.scale_rel_err(a, a64, ok64) <= max(parity.SCALE_RTOL, 2 * floor_a), (floor_a,)
+    assert parity.scale_rel_err(u, u64, ok64, floor=np.abs(a64)) <= max(parity.SCALE_RTOL, 2 * floor_u), (floor_u,)
+    if dist == "normal":
+        assert parity.scale_rel_err(a, ra, same[:, None]) <= parity.SCALE_RTOL
+        assert parity.scale_rel_err(u, ru, same[:, None], floor=np.abs(ra)) <= parity.SCALE_RTOL
+    # E is the block error of the kernel's OWN (alpha, mu, T) (gptq.py:158-159), bit for bit
+    assert np.array_equal(E, W[:, blk] - (a * T.astype(np.float32) + u))
+    np.testing.assert_allclose(E[same], rE[same], rtol=0, atol=2e-4 * float(np.abs(ra).max()))
     # per-row early exit does far fewer rounds than the reference's global loop
     _, _, _, g_iters = oracle.iterative_ternary_fitting(W[:, blk], *oracle.ternary_init(W[:, blk]), return_iters=True)
     assert iters.max() <= g_iters and iters.mean() < g_iters
