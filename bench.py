@@ -237,8 +237,18 @@ def main():
     hess_events = []
     results_keep = {}
 
+    if world > 1:
+        par.init_comm(ctx)
+    sharded_layer = par.ShardedLayer(ctx, block_size=128, percdamp=0.01)
+
     def quantize_model(record=False):
         for li in range(cfg["layers"]):
+            if world > 1:
+                # per layer: local Hessians -> NCCL all-reduce -> inverses dealt to ranks + broadcast -> row-slab sweeps
+                results_keep["last"] = sharded_layer.quantize(
+                    [(name, weights[li][name], acts[src]) for name, n, m, src in lins], use_ssr=True,
+                    hess_timing=hess_events if record else None)
+                continue
             for name, n, m, src in lins:
                 layer = LinearView(weights[li][name])
                 g = par.ShardedGPTQ(layer, ctx, block_size=128, percdamp=0.01)

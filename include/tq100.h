@@ -156,12 +156,28 @@ int tq_unpack2b(const uint8_t* packed, int64_t count, int8_t* T, void* stream);
  *   Hd    damped normalised H (AGA 'hessian');  Hraw raw accumulated H (AGA 'activations');
  *   static_perm int32 [m] for TQ_ORDER_STATIC, else NULL;
  *   Torig int8 [n,m], alpha/mu f32 [n, nb], perm int32 [m] (nb = ceil(m/block));
- *   workspace: tq_sweep_workspace_bytes(n, m, block) bytes. */
+ *   workspace: tq_sweep_workspace_bytes(n, m, block) bytes;
+ *   flags: TQ_SWEEP_ROW_SHARD = W holds one contiguous row slab of the layer and the other slabs are
+ *          swept by the other ranks of the communicator (tq_comm_init): with SSR the per-block column
+ *          statistics are all-reduced (2*rem+1 floats, NCCL, on `stream`) so every rank selects the
+ *          same block; sequential / static orders need no exchange. */
+#define TQ_SWEEP_ROW_SHARD 1
 int64_t tq_sweep_workspace_bytes(int64_t n, int64_t m, int64_t block);
 int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const float* Hd, const float* Hraw,
                    const float* Hinv, int64_t block, int order, int aga, int max_iter,
                    const int32_t* static_perm, int8_t* Torig, float* alpha, float* mu,
-                   int32_t* perm, void* workspace, int64_t workspace_bytes, void* stream);
+                   int32_t* perm, void* workspace, int64_t workspace_bytes, int flags, void* stream);
+
+/* ---- communicator for the row-sharded sweep ------------------------------------------
+ * One process per GPU.  Rank 0 calls tq_comm_unique_id (128 bytes, host), ships the bytes to the other
+ * ranks (torch.distributed broadcast), every rank calls tq_comm_init on its device.  NCCL is taken from
+ * the libnccl.so.2 already loaded in the process; the library itself does not link against it.
+ * tq_comm_ready returns the communicator size (0 = none). */
+int tq_comm_unique_id(void* out128_host);
+int tq_comm_init(const void* id128_host, int rank, int nranks);
+int tq_comm_ready(void);
+int tq_comm_destroy(void);
+int tq_comm_allreduce_f32(float* buf, int64_t count, void* stream);
 
 #ifdef __cplusplus
 }

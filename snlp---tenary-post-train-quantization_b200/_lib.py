@@ -14,6 +14,7 @@ F32, F16, BF16 = 0, 1, 2
 HESS_AUTO, HESS_FFMA, HESS_TCGEN05 = 0, 1, 2
 AGA_NONE, AGA_HESSIAN, AGA_ACTIVATIONS = 0, 1, 2
 ORDER_SEQUENTIAL, ORDER_SSR, ORDER_STATIC = 0, 1, 2
+SWEEP_ROW_SHARD = 1
 OP_INIT, OP_GRID, OP_ROUND, OP_ITF, OP_AGA = 0, 1, 2, 3, 4
 
 _i64 = ctypes.c_int64
@@ -45,7 +46,12 @@ _SIGNATURES = {
     "tq_unpack2b": (_int, [_ptr, _i64, _ptr, _ptr]),
     "tq_sweep_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "tq_sweep_layer": (_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _i64, _int, _int, _int, _ptr, _ptr,
-                              _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
+                              _ptr, _ptr, _ptr, _ptr, _i64, _int, _ptr]),
+    "tq_comm_unique_id": (_int, [_ptr]),
+    "tq_comm_init": (_int, [_ptr, _int, _int]),
+    "tq_comm_ready": (_int, []),
+    "tq_comm_destroy": (_int, []),
+    "tq_comm_allreduce_f32": (_int, [_ptr, _i64, _ptr]),
 }
 
 EXPORTS = tuple(_SIGNATURES)
@@ -112,5 +118,4 @@ def dtype_code(dt):
 
 def comm_ready():
     """True once the in-library NCCL communicator (row-sharded SSR statistics) is initialised."""
-    lib = load()
-    return hasattr(lib, "tq_comm_ready") and bool(lib.tq_comm_ready())
+    return load().tq_comm_ready() > 1

@@ -232,28 +232,36 @@ atq_stage_kernel(int op, const float* __restrict__ W, int64_t ldw, int n, int b,
 }
 
 // s1 = S 1, d = 1'S1 for one block.  HESSIAN: S = Hb'Hb (Hb = Hsrc[blk,blk], what gptq.py:147-150 feeds
-// quantizer.py:207); ACTIVATIONS: S = Hsrc[blk,blk] = (X'X)[blk,blk] (main.py:177-180).  One CTA.
-__global__ void __launch_bounds__(256)
+// quantizer.py:207); ACTIVATIONS: S = Hsrc[blk,blk] = (X'X)[blk,blk] (main.py:177-180).  One CTA of 32
+// warps; every output is a row-times-vector product of the gathered sub-block (warp per row, lanes along
+// the row).  Hsrc is exactly symmetric (tq_hessian_finalize / tq_symmetrize mirror the upper triangle), so
+// Hb'(Hb 1) is computed as Hb (Hb 1) with the same row-wise access.
+__global__ void __launch_bounds__(1024)
 aga_vector_kernel(const float* __restrict__ Hsrc, int64_t ldh, const int32_t* __restrict__ blk_idx, int col0,
                   int b, int mode, float* __restrict__ s1d) {
-    extern __shared__ float sh[];           // u[b], s1[b]
-    float* u = sh;
-    float* s1 = sh + b;
+    extern __shared__ float sh[];           // cols[b] (as int), u[b], s1[b]
+    int* cols = reinterpret_cast<int*>(sh);
+    float* u = sh + b;
+    float* s1 = sh + 2 * b;
     __shared__ float red[32];
-    auto col = [&](int p) { return blk_idx ? blk_idx[p] : col0 + p; };
-    for (int i = threadIdx.x; i < b; i += blockDim.x) {
-        const float* hrow = Hsrc + (int64_t)col(i) * ldh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int p = threadIdx.x; p < b; p += blockDim.x) cols[p] = blk_idx ? blk_idx[p] : col0 + p;
+    __syncthreads();
+    for (int i = warp; i < b; i += nwarp) {
+        const float* hrow = Hsrc + (int64_t)cols[i] * ldh;
         float s = 0.f;
-        for (int j = 0; j < b; ++j) s += hrow[col(j)];
-        u[i] = s;                            // row sums of the sub-block
+        for (int j = lane; j < b; j += 32) s += hrow[cols[j]];
+        s = warp_sum(s);
+        if (lane == 0) u[i] = s;             // row sums of the sub-block
     }
     __syncthreads();
     if (mode == TQ_AGA_HESSIAN) {
-        for (int j = threadIdx.x; j < b; j += blockDim.x) {
-            const int cj = col(j);
+        for (int i = warp; i < b; i += nwarp) {
+            const float* hrow = Hsrc + (int64_t)cols[i] * ldh;
             float s = 0.f;
-            for (int i = 0; i < b; ++i) s += Hsrc[(int64_t)col(i) * ldh + cj] * u[i];
-            s1[j] = s;                       // Hb' (Hb 1)
+            for (int j = lane; j < b; j += 32) s = fmaf(hrow[cols[j]], u[j], s);
+            s = warp_sum(s);
+            if (lane == 0) s1[i] = s;        // Hb (Hb 1)
         }
     } else {
         for (int j = threadIdx.x; j < b; j += blockDim.x) s1[j] = u[j];
@@ -265,10 +273,10 @@ aga_vector_kernel(const float* __restrict__ Hsrc, int64_t ldh, const int32_t* __
         part += s1[j];
     }
     part = warp_sum(part);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = part;
+    if (lane == 0) red[warp] = part;
     __syncthreads();
     if (threadIdx.x < 32) {
-        float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+        float v = (threadIdx.x < nwarp) ? red[threadIdx.x] : 0.f;
         v = warp_sum(v);
         if (threadIdx.x == 0) s1d[b] = v;
     }
@@ -294,7 +302,7 @@ int launch_atq_block(const float* W, int64_t ldw, int64_t n, const int32_t* blk_
 
 int launch_aga_vector(const float* Hsrc, int64_t ldh, const int32_t* blk_idx, int64_t col0, int64_t b, int mode,
                       float* s1d, cudaStream_t st) {
-    aga_vector_kernel<<<1, 256, 2 * b * sizeof(float), st>>>(Hsrc, ldh, blk_idx, (int)col0, (int)b, mode, s1d);
+    aga_vector_kernel<<<1, 1024, 3 * b * sizeof(float), st>>>(Hsrc, ldh, blk_idx, (int)col0, (int)b, mode, s1d);
     TQ_LAUNCH_CHECK("aga_vector_kernel");
     return 0;
 }

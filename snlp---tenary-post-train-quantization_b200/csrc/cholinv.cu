@@ -20,60 +20,142 @@ constexpr int CB = 128;            // panel width
 constexpr int CB_LD = CB + 1;      // shared-memory row stride
 constexpr int DIAG_THREADS = 512;
 
+// One CTA factors a 128x128 diagonal block and inverts its Cholesky factor, all in shared memory, in four
+// 32-column steps:  warp 0 factors the 32x32 diagonal sub-block with its rows in registers (pivots and
+// multipliers travel by shuffle), the rows below are solved against it one thread per row, the trailing
+// sub-blocks take the rank-32 update.  The inverse is built the same way: four warps invert the 32x32
+// diagonal sub-blocks, then the off-diagonal sub-blocks follow level by level as 32x32 products.
+constexpr int SB = 32;                 // sub-block width
+constexpr int NSB = CB / SB;           // 4
+
+__device__ __forceinline__ void diag_factor_32(float* S, int o, int nb, int k0, int* info, int lane) {
+    float a[SB];
+#pragma unroll
+    for (int c = 0; c < SB; ++c) a[c] = S[(o + lane) * CB_LD + o + c];
+#pragma unroll
+    for (int j = 0; j < SB; ++j) {
+        float pj = __shfl_sync(0xffffffffu, a[j], j);
+        if (!(pj > 0.f)) {                                   // also catches NaN
+            if (lane == 0 && o + j < nb) atomicCAS(info, 0, k0 + o + j + 1);
+            pj = 1.f;                                        // keep going so nothing downstream divides by zero
+        }
+        const float dj = sqrtf(pj);
+        const float l = (lane == j) ? dj : __fdiv_rn(a[j], dj);
+        a[j] = l;
+#pragma unroll
+        for (int c = j + 1; c < SB; ++c) {
+            const float lc = __shfl_sync(0xffffffffu, l, c);
+            if (lane >= c) a[c] = fmaf(-l, lc, a[c]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < SB; ++c) S[(o + lane) * CB_LD + o + c] = (c <= lane) ? a[c] : 0.f;
+}
+
 __global__ void __launch_bounds__(DIAG_THREADS)
 chol_diag_kernel(float* __restrict__ A, int64_t ld, int m, int k0, float* __restrict__ Dk, int* __restrict__ info) {
     extern __shared__ float sh[];
     float* S = sh;                       // [CB][CB_LD]  A_kk -> L_kk
     float* V = sh + CB * CB_LD;          // [CB][CB_LD]  L_kk^-1
-    const int tid = threadIdx.x;
+    float* Tm = sh + 2 * CB * CB_LD;     // [3][SB][SB+1] scratch for the off-diagonal inverse blocks
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nb = min(CB, m - k0);
     for (int e = tid; e < CB * CB; e += DIAG_THREADS) {
-        const int i = e / CB, j = e % CB;
+        const int i = e >> 7, j = e & (CB - 1);
         float v = (i == j) ? 1.f : 0.f;                          // identity padding for a ragged last panel
         if (i < nb && j < nb) v = (j <= i) ? A[(int64_t)(k0 + i) * ld + k0 + j] : 0.f;
         S[i * CB_LD + j] = v;
         V[i * CB_LD + j] = 0.f;
     }
     __syncthreads();
-    // right-looking Cholesky of the block
-    for (int j = 0; j < CB; ++j) {
-        if (tid == 0) {
-            float p = S[j * CB_LD + j];
-            if (!(p > 0.f)) {                                    // also catches NaN
-                if (j < nb) atomicCAS(info, 0, k0 + j + 1);
-                p = 1.f;                                         // keep going so nothing downstream divides by zero
+
+    // ---- L = chol(S), right-looking over 32-column steps
+    for (int d = 0; d < NSB; ++d) {
+        const int o = d * SB;
+        if (warp == 0) diag_factor_32(S, o, nb, k0, info, lane);
+        __syncthreads();
+        const int below = CB - o - SB;                           // rows under the diagonal sub-block
+        if (tid < below) {                                       // x L_dd' = a : one row per thread
+            float* row = S + (o + SB + tid) * CB_LD + o;
+            float x[SB];
+#pragma unroll
+            for (int j = 0; j < SB; ++j) {
+                float s = row[j];
+#pragma unroll
+                for (int k = 0; k < j; ++k) s = fmaf(-x[k], S[(o + j) * CB_LD + o + k], s);
+                x[j] = __fdiv_rn(s, S[(o + j) * CB_LD + o + j]);
             }
-            S[j * CB_LD + j] = sqrtf(p);
+#pragma unroll
+            for (int j = 0; j < SB; ++j) row[j] = x[j];
         }
         __syncthreads();
-        const float d = S[j * CB_LD + j];
-        for (int i = j + 1 + tid; i < CB; i += DIAG_THREADS) S[i * CB_LD + j] = __fdiv_rn(S[i * CB_LD + j], d);
-        __syncthreads();
-        const int t = CB - 1 - j;                                // trailing size
-        for (int e = tid; e < t * t; e += DIAG_THREADS) {
-            const int i = j + 1 + e / t, c = j + 1 + e % t;
-            if (c <= i) S[i * CB_LD + c] = fmaf(-S[i * CB_LD + j], S[c * CB_LD + j], S[i * CB_LD + c]);
+        if (below > 0) {                                         // trailing -= P P', 4 threads per row
+            const int r = o + SB + (tid >> 2);
+            if (r < CB) {
+                float pr[SB];
+#pragma unroll
+                for (int k = 0; k < SB; ++k) pr[k] = S[r * CB_LD + o + k];
+                for (int c = o + SB + (tid & 3); c <= r; c += 4) {
+                    float s = 0.f;
+#pragma unroll
+                    for (int k = 0; k < SB; ++k) s = fmaf(pr[k], S[c * CB_LD + o + k], s);
+                    S[r * CB_LD + c] -= s;
+                }
+            }
         }
         __syncthreads();
     }
-    // V = L^-1 : column c by forward substitution, 4 lanes per column share each dot product
-    {
-        const int c = tid >> 2, sub = tid & 3;
-        if (sub == 0) V[c * CB_LD + c] = __fdiv_rn(1.f, S[c * CB_LD + c]);
-        __syncwarp();
-        for (int i = 1; i < CB; ++i) {
-            float part = 0.f;
-            if (i > c)
-                for (int q = c + sub; q < i; q += 4) part = fmaf(S[i * CB_LD + q], V[q * CB_LD + c], part);
-            part += __shfl_xor_sync(0xffffffffu, part, 1);
-            part += __shfl_xor_sync(0xffffffffu, part, 2);
-            if (i > c && sub == 0) V[i * CB_LD + c] = __fdiv_rn(-part, S[i * CB_LD + i]);
-            __syncwarp();
+
+    // ---- V = L^-1: diagonal sub-blocks, one warp each, lane = column of the inverse
+    if (warp < NSB) {
+        const int o = warp * SB;
+        float x[SB];
+#pragma unroll
+        for (int i = 0; i < SB; ++i) {
+            float s = (i == lane) ? 1.f : 0.f;
+#pragma unroll
+            for (int k = 0; k < i; ++k) s = fmaf(-S[(o + i) * CB_LD + o + k], x[k], s);
+            x[i] = (i >= lane) ? __fdiv_rn(s, S[(o + i) * CB_LD + o + i]) : 0.f;
         }
+#pragma unroll
+        for (int i = 0; i < SB; ++i) V[(o + i) * CB_LD + o + lane] = x[i];
     }
     __syncthreads();
+    // off-diagonal sub-blocks, level by level:  V_ij = -V_ii * sum_{k=j}^{i-1} L_ik V_kj
+    for (int lev = 1; lev < NSB; ++lev) {
+        const int nblk = NSB - lev;                              // blocks (i, j) = (j + lev, j)
+        const int g = tid >> 7, t = tid & 127;                   // one 128-thread group per block
+        const int bj = g, bi = g + lev;
+        const int er = t >> 2, ec0 = (t & 3) * 8;                // each thread: row er, 8 columns
+        if (g < nblk) {
+            float acc[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+            for (int k = bj * SB; k < bi * SB; ++k) {
+                const float l = S[(bi * SB + er) * CB_LD + k];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] = fmaf(l, V[k * CB_LD + bj * SB + ec0 + q], acc[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) Tm[(g * SB + er) * (SB + 1) + ec0 + q] = acc[q];
+        }
+        __syncthreads();
+        if (g < nblk) {
+            float acc[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+            for (int k = 0; k <= er; ++k) {                      // V_ii is lower triangular
+                const float v = V[(bi * SB + er) * CB_LD + bi * SB + k];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] = fmaf(v, Tm[(g * SB + k) * (SB + 1) + ec0 + q], acc[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) V[(bi * SB + er) * CB_LD + bj * SB + ec0 + q] = -acc[q];
+        }
+        __syncthreads();
+    }
     for (int e = tid; e < CB * CB; e += DIAG_THREADS) {
-        const int i = e / CB, j = e % CB;
+        const int i = e >> 7, j = e & (CB - 1);
         Dk[e] = V[i * CB_LD + j];
         if (i < nb && j < nb && j <= i) A[(int64_t)(k0 + i) * ld + k0 + j] = S[i * CB_LD + j];
     }
@@ -227,7 +309,7 @@ extern "C" int tq_chol_inverse(float* Hinv, const float* Hd, int64_t m, float* w
     const int panels = (int)ceil_div(m, CB);
 
     static bool attr_set = false;
-    const int diag_smem = 2 * CB * CB_LD * (int)sizeof(float);
+    const int diag_smem = (2 * CB * CB_LD + 3 * SB * (SB + 1)) * (int)sizeof(float);
     if (!attr_set) {
         TQ_CUDA(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
         attr_set = true;

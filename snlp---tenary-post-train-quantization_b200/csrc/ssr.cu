@@ -225,6 +225,40 @@ ssr_select_kernel(const float* __restrict__ partials, int num_chunks, const floa
     for (int i = tid; i < block; i += SEL_THREADS) blk_idx[i] = rem_idx[(uint32_t)(win[i] & 0xffffffffu)];
 }
 
+// row-sharded sweep: fold this rank's per-chunk partials into one [2*rem + 1] vector (dot, sq, sum wbar^2),
+// in a fixed order, ready for the all-reduce across row shards
+__global__ void __launch_bounds__(256)
+ssr_fold_kernel(const float* __restrict__ partials, int num_chunks, const float* __restrict__ rowmean, int n, int rem,
+                float* __restrict__ folded) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < 2 * rem) {
+        float s = 0.f;
+        for (int c = 0; c < num_chunks; ++c) s += partials[(int64_t)c * 2 * rem + j];
+        folded[j] = s;
+    }
+    if (blockIdx.x == 0) {
+        __shared__ float red[8];
+        float s = 0.f;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(rowmean[i], rowmean[i], s);
+        s = warp_sum(s);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float v = (threadIdx.x < 8) ? red[threadIdx.x] : 0.f;
+            v = warp_sum(v);
+            if (threadIdx.x == 0) folded[2 * rem] = v;
+        }
+    }
+}
+
+int launch_ssr_fold(const float* partials, int64_t num_chunks, const float* rowmean, int64_t n, int64_t rem,
+                    float* folded, cudaStream_t st) {
+    ssr_fold_kernel<<<(unsigned)ceil_div(2 * rem, 256), 256, 0, st>>>(partials, (int)num_chunks, rowmean, (int)n,
+                                                                      (int)rem, folded);
+    TQ_LAUNCH_CHECK("ssr_fold_kernel");
+    return 0;
+}
+
 int launch_ssr_stats(const float* W, int64_t ldw, int64_t n, const int32_t* rem_idx, int64_t rem, float* rowmean,
                      float* partials, cudaStream_t st) {
     ssr_rowmean_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, st>>>(W, ldw, (int)n, rem_idx, (int)rem, rowmean);

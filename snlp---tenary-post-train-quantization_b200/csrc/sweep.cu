@@ -15,6 +15,9 @@ int launch_ssr_select(const float*, int64_t, const float*, int64_t, const float*
 int launch_err_feedback(float*, int64_t, int64_t, const float*, int64_t, const float*, int64_t, const int32_t*,
                         int64_t, int64_t, const int32_t*, int64_t, int64_t, cudaStream_t);
 int launch_unpermute(const int8_t*, int64_t, int64_t, const int32_t*, int8_t*, float*, cudaStream_t);
+int launch_ssr_fold(const float*, int64_t, const float*, int64_t, int64_t, float*, cudaStream_t);
+bool comm_active();
+int comm_allreduce_sum_f32(float*, int64_t, cudaStream_t);
 
 __global__ void iota_kernel(int32_t* __restrict__ a, int m) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -27,6 +30,7 @@ struct SweepWs {
     float* partials;
     float* sims;       // [2*m]: similarities + selection keys
     float* s1d;
+    float* folded;     // [2*m + 1] all-reduced SSR statistics (row-sharded sweep)
     int32_t* rem[2];
     int8_t* Tperm;
     int64_t bytes;
@@ -45,6 +49,7 @@ static SweepWs carve(void* base, int64_t n, int64_t m, int64_t block) {
     w.partials = reinterpret_cast<float*>(take(sizeof(float) * chunks * 2 * m));
     w.sims = reinterpret_cast<float*>(take(sizeof(float) * 2 * m));
     w.s1d = reinterpret_cast<float*>(take(sizeof(float) * (block + 1)));
+    w.folded = reinterpret_cast<float*>(take(sizeof(float) * (2 * m + 1)));
     w.rem[0] = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * m));
     w.rem[1] = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * m));
     w.Tperm = reinterpret_cast<int8_t*>(take(n * m));
@@ -61,7 +66,7 @@ extern "C" int64_t tq_sweep_workspace_bytes(int64_t n, int64_t m, int64_t block)
 extern "C" int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const float* Hd, const float* Hraw,
                               const float* Hinv, int64_t block, int order, int aga, int max_iter,
                               const int32_t* static_perm, int8_t* Torig, float* alpha, float* mu, int32_t* perm,
-                              void* workspace, int64_t workspace_bytes, void* stream) {
+                              void* workspace, int64_t workspace_bytes, int flags, void* stream) {
     using namespace tq;
     TQ_CHECK_ARG(W && Hinv && Torig && alpha && mu && perm && workspace, "tq_sweep_layer: null pointer");
     TQ_CHECK_ARG(n > 0 && m > 0 && ldw >= m && block >= 1 && block <= 512, "tq_sweep_layer: bad shape");
@@ -71,6 +76,9 @@ extern "C" int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const
     TQ_CHECK_ARG(aga == TQ_AGA_NONE || (aga == TQ_AGA_HESSIAN && Hd) || (aga == TQ_AGA_ACTIVATIONS && Hraw),
                  "tq_sweep_layer: AGA mode %d needs its Hessian (Hd for HESSIAN, Hraw for ACTIVATIONS)", aga);
     TQ_CHECK_ARG(max_iter >= 0, "tq_sweep_layer: max_iter < 0");
+    const bool sharded = (flags & TQ_SWEEP_ROW_SHARD) != 0;
+    TQ_CHECK_ARG(!sharded || order != TQ_ORDER_SSR || comm_active(),
+                 "tq_sweep_layer: TQ_SWEEP_ROW_SHARD with SSR needs the communicator (tq_comm_init)");
     cudaStream_t st = (cudaStream_t)stream;
     SweepWs ws = carve(workspace, n, m, block);
     if (ws.bytes > workspace_bytes) {
@@ -103,9 +111,17 @@ extern "C" int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const
                 TQ_CUDA(cudaMemcpyAsync(perm + done, ws.rem[cur], sizeof(int32_t) * rem, cudaMemcpyDeviceToDevice, st));
             } else {
                 if ((rc = launch_ssr_stats(W, ldw, n, ws.rem[cur], rem, ws.rowmean, ws.partials, st))) return rc;
-                if ((rc = launch_ssr_select(ws.partials, chunks, ws.rowmean, n, nullptr, ws.rem[cur], rem, block,
-                                            perm + done, ws.rem[cur ^ 1], ws.sims,
-                                            reinterpret_cast<uint32_t*>(ws.sims + m), st)))
+                if (sharded) {
+                    // rows are one shard of the layer: column statistics must cover every shard's rows
+                    if ((rc = launch_ssr_fold(ws.partials, chunks, ws.rowmean, n, rem, ws.folded, st))) return rc;
+                    if ((rc = comm_allreduce_sum_f32(ws.folded, 2 * rem + 1, st))) return rc;
+                    if ((rc = launch_ssr_select(ws.folded, 1, nullptr, n, ws.folded + 2 * rem, ws.rem[cur], rem, block,
+                                                perm + done, ws.rem[cur ^ 1], ws.sims,
+                                                reinterpret_cast<uint32_t*>(ws.sims + m), st)))
+                        return rc;
+                } else if ((rc = launch_ssr_select(ws.partials, chunks, ws.rowmean, n, nullptr, ws.rem[cur], rem, block,
+                                                   perm + done, ws.rem[cur ^ 1], ws.sims,
+                                                   reinterpret_cast<uint32_t*>(ws.sims + m), st)))
                     return rc;
                 cur ^= 1;
             }

@@ -78,6 +78,20 @@ class HessianState:
             self._upper_only = False
         return self.H
 
+    def damped(self, percdamp: float) -> torch.Tensor:
+        """gptq.py:94-98 only: Hd = H/nsamples + percdamp*mean(diag)*I (no inverse)."""
+        if self.nsamples <= 0:
+            raise RuntimeError("quantize() called before add_batch(): the Hessian is empty")
+        lib = _lib.load()
+        m, dev = self.columns, self.device
+        Hd = torch.empty((m, m), dtype=torch.float32, device=dev)
+        scratch = torch.empty(8, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.tq_hessian_finalize(_lib.ptr(Hd), _lib.ptr(self.H), m, float(self.nsamples), float(percdamp),
+                                               _lib.ptr(scratch), _lib.stream()), "tq_hessian_finalize")
+        scratch.record_stream(torch.cuda.current_stream(dev))
+        return Hd
+
     def damped_inverse(self, percdamp: float):
         """gptq.py:94-106: (Hd, Hinv, info) with Hd = H/nsamples + percdamp*mean(diag)*I and
         Hinv = cholesky_inverse(cholesky(Hd)); ``info`` is a device int (0 = ok)."""
@@ -129,6 +143,7 @@ class GPTQ:
         self.perm = None
         self.T_int8 = None
         self.info = None
+        self.sweep_flags = 0          # _lib.SWEEP_ROW_SHARD when this object sweeps one row slab of the layer
 
     # the reference exposes H and nsamples as plain attributes (gptq.py:50-51)
     @property
@@ -189,7 +204,7 @@ class GPTQ:
                 _lib.check(lib.tq_sweep_layer(_lib.ptr(W), W.stride(0), n, m, _lib.ptr(Hd), _lib.ptr(self.state.H),
                                               _lib.ptr(hinv), b, order_code, _AGA[aga], int(max_iter),
                                               _lib.ptr(static_perm), _lib.ptr(T8), _lib.ptr(alpha), _lib.ptr(mu),
-                                              _lib.ptr(perm), _lib.ptr(ws), ws_bytes, _lib.stream()),
+                                              _lib.ptr(perm), _lib.ptr(ws), ws_bytes, int(self.sweep_flags), _lib.stream()),
                            "tq_sweep_layer")
             for t in (W, ws):
                 t.record_stream(torch.cuda.current_stream(dev))

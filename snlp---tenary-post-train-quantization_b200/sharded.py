@@ -43,6 +43,24 @@ class ShardContext:
         return min(n, lo_g * 4), min(n, hi_g * 4)
 
 
+def init_comm(ctx: ShardContext):
+    """Create the in-library NCCL communicator (one per process): rank 0 makes the id, torch.distributed
+    ships the 128 bytes, every rank joins on its own device."""
+    import ctypes
+    lib = _lib.load()
+    if ctx.world == 1 or lib.tq_comm_ready():
+        return
+    buf = (ctypes.c_ubyte * 128)()
+    if ctx.rank == 0:
+        _lib.check(lib.tq_comm_unique_id(buf), "tq_comm_unique_id")
+    t = torch.tensor(list(buf), dtype=torch.uint8, device=ctx.device)
+    dist.broadcast(t, src=0, group=ctx.group)
+    raw = bytes(t.cpu().tolist())
+    cbuf = (ctypes.c_ubyte * 128).from_buffer_copy(raw)
+    with torch.cuda.device(ctx.device):
+        _lib.check(lib.tq_comm_init(cbuf, ctx.rank, ctx.world), "tq_comm_init")
+
+
 class ShardedGPTQ:
     """GPTQ over a ShardContext.  With world == 1 this is exactly ``GPTQ``."""
 
@@ -81,7 +99,7 @@ class ShardedGPTQ:
         lo, hi = self.ctx.row_range(self.rows)
         shard = GPTQ(LinearView(self.layer.weight.data[lo:hi]), self.block_size, self.percdamp,
                      hessian=self.inner.state)
-        shard.comm = self.ctx
+        shard.sweep_flags = _lib.SWEEP_ROW_SHARD
         alpha, mu, T, perm = shard.quantize(use_ssr=use_ssr, aga=aga, order=order, max_iter=max_iter)
         self.shard = shard
         if not gather:
@@ -94,3 +112,66 @@ class ShardedGPTQ:
             dist.all_gather(parts, t.contiguous(), group=self.ctx.group)
             outs.append(torch.cat(parts, dim=0))
         return outs[0], outs[1], outs[2], perm
+
+
+class ShardedLayer:
+    """One transformer layer's linears over a ShardContext (the multi-GPU form of the per-layer loop of
+    main.py:289-299):
+      1. every rank accumulates each linear's H over ITS calibration samples (tcgen05 SYRK);
+      2. one NCCL all-reduce per H (+ one for the token counts) -> identical H everywhere;
+      3. the damped Cholesky inverses are dealt round-robin to the ranks and broadcast (H^-1 is then
+         replicated, as the sweep needs it);
+      4. every rank sweeps its contiguous row slab of every linear; with SSR the per-block column
+         statistics are all-reduced inside the C driver loop (in-library NCCL communicator)."""
+
+    def __init__(self, ctx: ShardContext, block_size: int = 128, percdamp: float = 0.01):
+        self.ctx, self.block_size, self.percdamp = ctx, block_size, percdamp
+
+    def quantize(self, linears, use_ssr: bool = True, aga: str = "hessian", max_iter: int = 100, hess_timing=None):
+        """linears: [(name, W (n, m) replicated on every rank, X_local (this rank's samples, (.., m)))].
+        Returns [(name, alpha_slab, mu_slab, T_int8_slab, perm, (row_lo, row_hi))].
+        hess_timing: optional list that receives (start_event, end_event, tokens, m) per Hessian launch."""
+        ctx = self.ctx
+        states = []
+        for _, W, X in linears:
+            st = HessianState(W.shape[1], W.device)
+            if hess_timing is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            st.add_batch(X)
+            if hess_timing is not None:
+                e1.record()
+                hess_timing.append((e0, e1, X.numel() // X.shape[-1], W.shape[1]))
+            states.append(st)
+        if ctx.world > 1:
+            counts = torch.tensor([st.nsamples for st in states], dtype=torch.int64, device=ctx.device)
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=ctx.group)
+            for st, c in zip(states, counts.tolist()):
+                dist.all_reduce(st.H, op=dist.ReduceOp.SUM, group=ctx.group)
+                st.nsamples = int(c)
+                st._cache.clear()
+            # inverses: owner computes, everyone receives
+            pending = []
+            for i, st in enumerate(states):
+                owner = i % ctx.world
+                m = st.columns
+                if owner == ctx.rank:
+                    Hd, Hinv, info = st.damped_inverse(self.percdamp)
+                else:
+                    Hd = st.damped(self.percdamp)
+                    Hinv = torch.empty((m, m), dtype=torch.float32, device=ctx.device)
+                    info = torch.zeros(1, dtype=torch.int32, device=ctx.device)
+                pending.append((st, owner, Hd, Hinv, info))
+            for st, owner, Hd, Hinv, info in pending:
+                dist.broadcast(Hinv, src=owner, group=ctx.group)
+                dist.broadcast(info, src=owner, group=ctx.group)
+                st._cache[float(self.percdamp)] = (Hd, Hinv, info)
+        out = []
+        for (name, W, _), st in zip(linears, states):
+            lo, hi = ctx.row_range(W.shape[0])
+            g = GPTQ(LinearView(W[lo:hi]), self.block_size, self.percdamp, hessian=st)
+            if ctx.world > 1:
+                g.sweep_flags = _lib.SWEEP_ROW_SHARD
+            alpha, mu, _, perm = g.quantize(use_ssr=use_ssr, aga=aga, max_iter=max_iter)
+            out.append((name, alpha, mu, g.T_int8, perm, (lo, hi)))
+        return out

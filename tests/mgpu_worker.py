@@ -1,0 +1,79 @@
+"""torchrun worker for the multi-GPU parity test: sharded path (N ranks) vs the single-GPU path on rank 0."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+import parity  # noqa: E402
+import synth  # noqa: E402
+import tq100  # noqa: E402
+from tq100 import sharded  # noqa: E402
+from tq100.pipeline import LinearView  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ctx = sharded.ShardContext(rank, world, dev)
+    sharded.init_comm(ctx)
+    assert tq100._lib.comm_ready()
+
+    samples, seq = 8, 256
+    shapes = [("a", 512, 1024), ("b", 384, 1024), ("c", 1024, 640)]
+    lins, full = [], {}
+    for name, n, m in shapes:
+        W = synth.make_weight(n, m, seed=hash(name) % 1000)
+        X = synth.make_activations(samples, seq, m, seed=hash(name) % 1000 + 1, lam=0.5)
+        full[name] = (W, X)
+        Xl = torch.from_numpy(X[ctx.my_samples(samples)]).to(dev)
+        lins.append((name, torch.from_numpy(W).to(dev), Xl))
+    layer = sharded.ShardedLayer(ctx)
+    for use_ssr in (False, True):
+        out = layer.quantize(lins, use_ssr=use_ssr)
+        for (name, alpha, mu, T8, perm, (lo, hi)) in out:
+            n = full[name][0].shape[0]
+            # gather slabs on every rank (pad to equal size for all_gather)
+            rows = [sharded.ShardContext(r, world).row_range(n) for r in range(world)]
+            mx = max(b - a for a, b in rows)
+
+            def gather(t):
+                pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+                pad[: t.shape[0]] = t
+                parts = [torch.empty_like(pad) for _ in range(world)]
+                dist.all_gather(parts, pad)
+                return torch.cat([p[: b - a] for p, (a, b) in zip(parts, rows)], 0)
+
+            A, U, TT = gather(alpha.float().contiguous()), gather(mu.float().contiguous()), gather(T8)
+            perms = [torch.empty_like(perm) for _ in range(world)]
+            dist.all_gather(perms, perm)
+            assert all(torch.equal(p, perms[0]) for p in perms), f"{name}: ranks chose different column orders"
+            if rank == 0:
+                W, X = full[name]
+                g = tq100.GPTQ(LinearView(torch.from_numpy(W).to(dev)))
+                g.add_batch(torch.from_numpy(X).to(dev))
+                a1, u1, T1, p1 = g.quantize(use_ssr=use_ssr)
+                got = dict(alpha=A.cpu().numpy(), mu=U.cpu().numpy(), T=TT.cpu().numpy(), perm=perm.cpu().numpy())
+                ref = dict(alpha=a1.cpu().numpy(), mu=u1.cpu().numpy(), T=T1.cpu().numpy(), perm=p1.cpu().numpy())
+                same_perm = np.array_equal(got["perm"], ref["perm"])
+                agree = parity.code_agreement(got["T"], ref["T"])
+                print(f"[mgpu] {name} ssr={use_ssr}: perm equal={same_perm} code agreement={agree:.6f}", flush=True)
+                if not use_ssr or same_perm:
+                    parity.assert_layer_parity(got, ref, what=f"{name}/ssr={use_ssr}")
+                else:
+                    assert set(got["perm"][:128].tolist()) == set(ref["perm"][:128].tolist())
+    dist.barrier()
+    if rank == 0:
+        print("MGPU_OK", flush=True)
+    tq100._lib.load().tq_comm_destroy()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
