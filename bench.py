@@ -216,11 +216,12 @@ def main():
     lam, r = 0.5, 64
     acts = {}
     my_samples = ctx.my_samples(SAMPLES)                       # calibration samples of this rank
-    for key, width in (("attn_in", cfg["d"]), ("o_in", cfg["d"]), ("mlp_in", cfg["d"]), ("down_in", cfg["ffn"])):
+    for ki, (key, width) in enumerate((("attn_in", cfg["d"]), ("o_in", cfg["d"]), ("mlp_in", cfg["d"]),
+                                       ("down_in", cfg["ffn"]))):
         B = torch.randn((r, width), device=dev, generator=gen)
         x = torch.empty((len(my_samples), SEQ, width), device=dev, dtype=torch.float16)
         for j, s in enumerate(my_samples):
-            g2 = torch.Generator(device=dev).manual_seed(100000 + 1000 * (hash(key) % 97) + s)
+            g2 = torch.Generator(device=dev).manual_seed(100000 + 1000 * ki + s)
             z = torch.randn((SEQ, width), device=dev, generator=g2)
             f = torch.randn((SEQ, r), device=dev, generator=g2)
             x[j] = (z + (lam / r ** 0.5) * (f @ B)).to(torch.float16)
@@ -228,8 +229,8 @@ def main():
     weights = []
     for li in range(cfg["layers"]):
         ws = {}
-        for name, n, m, _ in lins:
-            gw = torch.Generator(device=dev).manual_seed(7 * li + hash(name) % 1000)
+        for wi, (name, n, m, _) in enumerate(lins):
+            gw = torch.Generator(device=dev).manual_seed(1000 * li + wi)          # identical on every rank
             ws[name] = torch.randn((n, m), device=dev, generator=gw) * 0.02
         weights.append(ws)
     torch.cuda.synchronize()

@@ -28,9 +28,9 @@ def main():
     samples, seq = 8, 256
     shapes = [("a", 512, 1024), ("b", 384, 1024), ("c", 1024, 640)]
     lins, full = [], {}
-    for name, n, m in shapes:
-        W = synth.make_weight(n, m, seed=hash(name) % 1000)
-        X = synth.make_activations(samples, seq, m, seed=hash(name) % 1000 + 1, lam=0.5)
+    for si, (name, n, m) in enumerate(shapes):
+        W = synth.make_weight(n, m, seed=500 + 10 * si)          # NOT hash(name): str hashes differ per process
+        X = synth.make_activations(samples, seq, m, seed=501 + 10 * si, lam=0.5)
         full[name] = (W, X)
         Xl = torch.from_numpy(X[ctx.my_samples(samples)]).to(dev)
         lins.append((name, torch.from_numpy(W).to(dev), Xl))
