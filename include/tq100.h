@@ -137,6 +137,17 @@ int tq_err_feedback(float* W, int64_t ldw, int64_t n, const float* E, int64_t ld
                     const float* Hinv, int64_t ldh, const int32_t* blk_idx, int64_t blk0, int64_t b,
                     const int32_t* rem_idx, int64_t rem0, int64_t rem, void* stream);
 
+/* Tensor-core form of the same update: E C as a 3xTF32 tcgen05 GEMM (hi*hi' + hi*lo' + lo*hi', fp32
+ * accumulate in TMEM), fp32-faithful to ~2^-21 relative per product.  workspace:
+ * tq_err_feedback_tc_workspace_floats(n, b, rem) floats, 16-byte aligned.  tq_split_tf32 writes the
+ * (hi, lo) split of a row-major matrix (hi = low 13 mantissa bits cleared, lo = x - hi). */
+int64_t tq_err_feedback_tc_workspace_floats(int64_t n, int64_t b, int64_t rem);
+int tq_err_feedback_tc(float* W, int64_t ldw, int64_t n, const float* E, int64_t lde,
+                       const float* Hinv, int64_t ldh, const int32_t* blk_idx, int64_t blk0, int64_t b,
+                       const int32_t* rem_idx, int64_t rem0, int64_t rem, float* workspace, void* stream);
+int tq_split_tf32(const float* x, int64_t ld, int64_t rows, int64_t cols, float* hi, float* lo,
+                  int64_t ld_out, void* stream);
+
 /* ---- A9-A11  epilogue, dequant, 2-bit codec ---------------------------------------------------
  * Tperm holds block k's codes at columns [k*block, ...) in sweep order; Torig[:, perm[p]] = Tperm[:, p]
  * (gptq.py:155 stores T in ORIGINAL positions).  Tf32 optional float copy (gptq.py:109). */
@@ -162,6 +173,7 @@ int tq_unpack2b(const uint8_t* packed, int64_t count, int8_t* T, void* stream);
  *          statistics are all-reduced (2*rem+1 floats, NCCL, on `stream`) so every rank selects the
  *          same block; sequential / static orders need no exchange. */
 #define TQ_SWEEP_ROW_SHARD 1
+#define TQ_SWEEP_FFMA_FEEDBACK 2   /* error feedback on the fp32 CUDA cores instead of the 3xTF32 tcgen05 GEMM */
 int64_t tq_sweep_workspace_bytes(int64_t n, int64_t m, int64_t block);
 int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const float* Hd, const float* Hraw,
                    const float* Hinv, int64_t block, int order, int aga, int max_iter,

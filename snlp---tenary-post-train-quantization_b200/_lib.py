@@ -15,6 +15,7 @@ HESS_AUTO, HESS_FFMA, HESS_TCGEN05 = 0, 1, 2
 AGA_NONE, AGA_HESSIAN, AGA_ACTIVATIONS = 0, 1, 2
 ORDER_SEQUENTIAL, ORDER_SSR, ORDER_STATIC = 0, 1, 2
 SWEEP_ROW_SHARD = 1
+SWEEP_FFMA_FEEDBACK = 2
 OP_INIT, OP_GRID, OP_ROUND, OP_ITF, OP_AGA = 0, 1, 2, 3, 4
 
 _i64 = ctypes.c_int64
@@ -39,6 +40,9 @@ _SIGNATURES = {
                             _ptr, _i64, _ptr, _ptr]),
     "tq_atq_stage": (_int, [_int, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _int, _ptr, _ptr, _ptr, _ptr]),
     "tq_err_feedback": (_int, [_ptr, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _ptr, _i64, _i64, _ptr]),
+    "tq_err_feedback_tc_workspace_floats": (_i64, [_i64, _i64, _i64]),
+    "tq_err_feedback_tc": (_int, [_ptr, _i64, _i64, _ptr, _i64, _ptr, _i64, _ptr, _i64, _i64, _ptr, _i64, _i64, _ptr, _ptr]),
+    "tq_split_tf32": (_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _i64, _ptr]),
     "tq_unpermute_codes": (_int, [_ptr, _i64, _i64, _ptr, _ptr, _ptr, _ptr]),
     "tq_dequant": (_int, [_ptr, _ptr, _i64, _ptr, _i64, _i64, _ptr, _i64, _ptr, _ptr]),
     "tq_pack2b": (_int, [_ptr, _i64, _ptr, _ptr]),

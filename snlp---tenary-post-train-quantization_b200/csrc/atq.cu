@@ -157,17 +157,32 @@ struct Row {
         }
     }
 
-    // gptq.py:158-159
-    __device__ __forceinline__ void store_error(float* __restrict__ erow, int b, float alpha, float mu, bool vec_ok) const {
-        float ev[EPL];
+    // gptq.py:158-159.  With erow_lo the error is written as the (hi, lo) tf32 split the tensor-core feedback
+    // GEMM consumes (hi = low 13 mantissa bits cleared, lo = e - hi, both exact), else as plain fp32.
+    __device__ __forceinline__ void store_error(float* __restrict__ erow, float* __restrict__ erow_lo, int b, float alpha,
+                                                float mu, bool vec_ok) const {
+        float ev[EPL], el[EPL];
 #pragma unroll
-        for (int e = 0; e < EPL; ++e) ev[e] = __fsub_rn(w[e], __fadd_rn(__fmul_rn(alpha, (float)t[e]), mu));
+        for (int e = 0; e < EPL; ++e) {
+            ev[e] = __fsub_rn(w[e], __fadd_rn(__fmul_rn(alpha, (float)t[e]), mu));
+            el[e] = 0.f;
+            if (erow_lo != nullptr) {
+                const float hi = __uint_as_float(__float_as_uint(ev[e]) & 0xFFFFE000u);
+                el[e] = __fsub_rn(ev[e], hi);
+                ev[e] = hi;
+            }
+        }
         if (EPL == 4 && vec_ok && (p0 + 3 < b)) {
             *reinterpret_cast<float4*>(erow + p0) = make_float4(ev[0], ev[1 % EPL], ev[2 % EPL], ev[3 % EPL]);
+            if (erow_lo != nullptr)
+                *reinterpret_cast<float4*>(erow_lo + p0) = make_float4(el[0], el[1 % EPL], el[2 % EPL], el[3 % EPL]);
         } else {
 #pragma unroll
             for (int e = 0; e < EPL; ++e)
-                if (valid[e]) erow[p0 + e] = ev[e];
+                if (valid[e]) {
+                    erow[p0 + e] = ev[e];
+                    if (erow_lo != nullptr) erow_lo[p0 + e] = el[e];
+                }
         }
     }
 };
@@ -177,7 +192,7 @@ __global__ void __launch_bounds__(256)
 atq_block_kernel(const float* __restrict__ W, int64_t ldw, int n, const int32_t* __restrict__ blk_idx, int col0,
                  int b, const float* __restrict__ s1d, int max_iter, int8_t* __restrict__ T, int64_t ldt,
                  float* __restrict__ alpha_out, float* __restrict__ mu_out, int64_t ld_am,
-                 float* __restrict__ E, int64_t lde, int32_t* __restrict__ iters_out) {
+                 float* __restrict__ E, float* __restrict__ E_lo, int64_t lde, int32_t* __restrict__ iters_out) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= n) return;
@@ -195,7 +210,9 @@ atq_block_kernel(const float* __restrict__ W, int64_t ldw, int n, const int32_t*
     }
     r.store_codes(T + (int64_t)row * ldt, b, ((ldt & 3) == 0) && ((reinterpret_cast<uintptr_t>(T) & 3) == 0));
     if (E != nullptr)
-        r.store_error(E + (int64_t)row * lde, b, alpha, mu, ((lde & 3) == 0) && ((reinterpret_cast<uintptr_t>(E) & 15) == 0));
+        r.store_error(E + (int64_t)row * lde, E_lo ? E_lo + (int64_t)row * lde : nullptr, b, alpha, mu,
+                      ((lde & 3) == 0) && ((reinterpret_cast<uintptr_t>(E) & 15) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(E_lo) & 15) == 0));
 }
 
 // The individual stages of the quantizer API (not on the sweep's path): one op per launch.
@@ -284,12 +301,12 @@ aga_vector_kernel(const float* __restrict__ Hsrc, int64_t ldh, const int32_t* __
 
 int launch_atq_block(const float* W, int64_t ldw, int64_t n, const int32_t* blk_idx, int64_t col0, int64_t b,
                      const float* s1d, int max_iter, int8_t* T, int64_t ldt, float* alpha, float* mu,
-                     int64_t ld_am, float* E, int64_t lde, int32_t* iters, cudaStream_t st) {
+                     int64_t ld_am, float* E, float* E_lo, int64_t lde, int32_t* iters, cudaStream_t st) {
     const int warps = 8;
     dim3 grid((unsigned)ceil_div(n, warps)), block(warps * 32);
 #define TQ_ATQ_CASE(EPL)                                                                                      \
     atq_block_kernel<EPL><<<grid, block, 0, st>>>(W, ldw, (int)n, blk_idx, (int)col0, (int)b, s1d, max_iter, \
-                                                  T, ldt, alpha, mu, ld_am, E, lde, iters)
+                                                  T, ldt, alpha, mu, ld_am, E, E_lo, lde, iters)
     if (b <= 32) TQ_ATQ_CASE(1);
     else if (b <= 64) TQ_ATQ_CASE(2);
     else if (b <= 128) TQ_ATQ_CASE(4);
@@ -317,7 +334,7 @@ extern "C" int tq_atq_block(const float* W, int64_t ldw, int64_t n, const int32_
     TQ_CHECK_ARG(n > 0 && b > 0 && b <= 512, "tq_atq_block: need n > 0 and 1 <= block <= 512 (got n=%lld b=%lld)",
                  (long long)n, (long long)b);
     TQ_CHECK_ARG(ldt >= b && ld_am >= 1 && (E == nullptr || lde >= b) && max_iter >= 0, "tq_atq_block: bad strides");
-    return launch_atq_block(W, ldw, n, blk_idx, col0, b, s1d, max_iter, T, ldt, alpha, mu, ld_am, E, lde, iters,
+    return launch_atq_block(W, ldw, n, blk_idx, col0, b, s1d, max_iter, T, ldt, alpha, mu, ld_am, E, nullptr, lde, iters,
                             (cudaStream_t)stream);
 }
 

@@ -1,0 +1,396 @@
+// fp32-faithful tensor-core GEMM for the fp32 stages:  C (op)= A B'  with A [M, K] and B [N, K] both K-major fp32.
+//
+// tcgen05 has no fp32 MMA; kind::tf32 keeps 11 significant bits of each operand.  Every operand is therefore
+// supplied as a (hi, lo) pair prepared by the producing kernel:  hi = x with the low 13 mantissa bits cleared
+// (exactly representable in tf32), lo = x - hi (exact in fp32), and three MMAs accumulate
+//     hi*hi' + hi*lo' + lo*hi'     in fp32 in TMEM
+// (the dropped lo*lo' term and the tf32 rounding of lo are O(2^-22) relative -- fp32 FFMA class; measured
+// against the fp32 CUDA-core kernels in tests/).  Used by
+//   error feedback (gptq.py:173-186)     W[:, rem] -= E C,  A = E, B = C' (built by feedback_coef_kernel)
+//   potrf trailing update                A_ij -= L_ik L_jk'
+//   trtri update                         R_i,: -= L_ik X_k,:
+//   lauum                                Hinv = Y Y' with Y = (L^-1)'
+//
+//   tile 128 x 128, K slabs of 32 floats (one 128-byte swizzled row), 3 smem stages x (A_hi, A_lo, B_hi, B_lo) x 16 KB
+//   TMEM: 2 accumulators x 128 columns; persistent CTAs; roles as in hessian_tc.cu
+//   epilogue: TMEM -> registers -> global read-modify-write (the RMW of C is the dominant, compulsory traffic:
+//   8 bytes per element per call at K = 128, i.e. HBM-bound -- SURVEY 8d)
+#include "tc_common.cuh"
+
+namespace tq {
+
+constexpr int GX_BM = 128, GX_BN = 128, GX_BK = 32, GX_STAGES = 3, GX_UMMA_K = 8;
+constexpr int GX_SLAB = GX_BM * GX_BK * 4;            // 16384
+constexpr int GX_STAGE_BYTES = 4 * GX_SLAB;           // 65536
+constexpr int GX_THREADS = 256;
+constexpr int GX_SMEM = GX_STAGES * GX_STAGE_BYTES + 256 + 1024;
+constexpr int GX_TMEM_COLS = 256;
+
+enum GxMode {
+    GX_FEEDBACK = 0,      // all tiles; C[r, colmap(j)] -= acc
+    GX_SUB_LOWER = 1,     // tiles bi >= bj; C[r, c] -= acc for c <= r  (potrf trailing update)
+    GX_SUB_RECT = 2,      // all tiles; C[r, c] -= acc                  (trtri update)
+    GX_STORE_UPPER = 3    // tiles bi <= bj, K range starts at the tile's first column; C[r, c] = acc (lauum)
+};
+
+struct GxProblem {
+    int M, N, K;            // C is M x N, contraction length K
+    int mt, nt, tiles;      // tile grid and number of scheduled tiles
+    int mode;
+    float* C;
+    int64_t ldc;
+    const int32_t* col_idx; // FEEDBACK: absolute column of remaining position j (NULL: col0 + j)
+    int col0;
+};
+
+__device__ __forceinline__ void gx_decode(const GxProblem& p, int t, int& bi, int& bj) {
+    if (p.mode == GX_SUB_LOWER) {
+        int j = 0;
+        for (;; ++j) {
+            const int cnt = p.mt - j;
+            if (t < cnt) break;
+            t -= cnt;
+        }
+        bj = j;
+        bi = j + t;
+    } else if (p.mode == GX_STORE_UPPER) {
+        int j = 0;
+        for (;; ++j) {
+            const int cnt = min(p.mt, j + 1);
+            if (t < cnt) break;
+            t -= cnt;
+        }
+        bj = j;
+        bi = t;
+    } else {
+        bj = t / p.mt;
+        bi = t - bj * p.mt;
+    }
+}
+
+// K-major, 128B-swizzled slab [128 rows x 32 floats]: 8 rows x 128 B per swizzle atom, next 8 rows at +1024 B
+__device__ __forceinline__ uint64_t gx_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(GX_THREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
+                   const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
+                   const GxProblem p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_bar = s_base + GX_STAGES * GX_STAGE_BYTES;
+    auto full_bar = [&](int s) { return s_bar + 8 * s; };
+    auto empty_bar = [&](int s) { return s_bar + 8 * (GX_STAGES + s); };
+    auto tfull_bar = [&](int a) { return s_bar + 8 * (2 * GX_STAGES + a); };
+    auto tempty_bar = [&](int a) { return s_bar + 8 * (2 * GX_STAGES + 2 + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + GX_STAGES * GX_STAGE_BYTES + 8 * (2 * GX_STAGES + 4));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ah) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_al) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bh) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bl) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < GX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(smem_u32(tmem_slot), GX_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tcgen05 instruction descriptor (kind::tf32): D = f32, A/B = TF32, both K-major, N = 128, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(GX_BN >> 3) << 17) | ((uint32_t)(GX_BM >> 4) << 24);
+
+    auto k_begin_of = [&](int bj) { return (p.mode == GX_STORE_UPPER) ? bj * GX_BN : 0; };
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer =====
+        int stage = 0, phase = 0;
+        for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+            int bi, bj;
+            gx_decode(p, t, bi, bj);
+            for (int k = k_begin_of(bj); k < p.K; k += GX_BK) {
+                mbar_wait(empty_bar(stage), phase ^ 1);
+                const uint32_t s0 = s_base + stage * GX_STAGE_BYTES;
+                mbar_expect_tx(full_bar(stage), GX_STAGE_BYTES);
+                tma_load_2d(s0 + 0 * GX_SLAB, &map_ah, full_bar(stage), k, bi * GX_BM);
+                tma_load_2d(s0 + 1 * GX_SLAB, &map_al, full_bar(stage), k, bi * GX_BM);
+                tma_load_2d(s0 + 2 * GX_SLAB, &map_bh, full_bar(stage), k, bj * GX_BN);
+                tma_load_2d(s0 + 3 * GX_SLAB, &map_bl, full_bar(stage), k, bj * GX_BN);
+                if (++stage == GX_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ===== MMA issuer: hi*hi' + hi*lo' + lo*hi' =====
+        int stage = 0, phase = 0, n_item = 0;
+        for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++n_item) {
+            int bi, bj;
+            gx_decode(p, t, bi, bj);
+            const int acc = n_item & 1;
+            mbar_wait(tempty_bar(acc), ((n_item >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * GX_BN;
+            const int kb0 = k_begin_of(bj);
+            bool first = true;
+            for (int k = kb0; k < p.K; k += GX_BK) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                const uint32_t s0 = s_base + stage * GX_STAGE_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < GX_BK / GX_UMMA_K; ++kk) {
+                    const uint32_t off = kk * GX_UMMA_K * 4;                 // 32 bytes along K inside the swizzled row
+                    const uint64_t ah = gx_desc(s0 + 0 * GX_SLAB + off), al = gx_desc(s0 + 1 * GX_SLAB + off);
+                    const uint64_t bh = gx_desc(s0 + 2 * GX_SLAB + off), bl = gx_desc(s0 + 3 * GX_SLAB + off);
+                    umma_tf32(tmem_d, al, bh, idesc, first ? 0u : 1u);
+                    first = false;
+                    umma_tf32(tmem_d, ah, bl, idesc, 1u);
+                    umma_tf32(tmem_d, ah, bh, idesc, 1u);
+                }
+                umma_commit(empty_bar(stage));
+                if (k + GX_BK >= p.K) umma_commit(tfull_bar(acc));
+                if (++stage == GX_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM -> registers -> global read-modify-write =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int n_item = 0;
+        for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++n_item) {
+            int bi, bj;
+            gx_decode(p, t, bi, bj);
+            const int acc = n_item & 1;
+            mbar_wait(tfull_bar(acc), (n_item >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * GX_BN;
+            const int r = bi * GX_BM + row;
+            float* crow = p.C + (int64_t)r * p.ldc;
+            for (int cg = 0; cg < GX_BN / 32; ++cg) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + cg * 32, v);
+                tmem_ld_wait();
+                if (cg == GX_BN / 32 - 1) {
+                    tc_fence_before();
+                    mbar_arrive(tempty_bar(acc));
+                }
+                const int j0 = bj * GX_BN + cg * 32;
+                if (r >= p.M || j0 >= p.N) continue;
+                if (p.mode == GX_FEEDBACK) {
+                    if (p.col_idx == nullptr) {
+                        const int c0 = p.col0 + j0;
+                        if (j0 + 32 <= p.N && ((c0 & 3) == 0) && ((p.ldc & 3) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0)) {
+                            float4* dst = reinterpret_cast<float4*>(crow + c0);
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                float4 w = dst[c];
+                                w.x = __fsub_rn(w.x, __uint_as_float(v[4 * c]));
+                                w.y = __fsub_rn(w.y, __uint_as_float(v[4 * c + 1]));
+                                w.z = __fsub_rn(w.z, __uint_as_float(v[4 * c + 2]));
+                                w.w = __fsub_rn(w.w, __uint_as_float(v[4 * c + 3]));
+                                dst[c] = w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 32; ++c)
+                                if (j0 + c < p.N) crow[c0 + c] = __fsub_rn(crow[c0 + c], __uint_as_float(v[c]));
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c)
+                            if (j0 + c < p.N) {
+                                float* d = crow + p.col_idx[j0 + c];
+                                *d = __fsub_rn(*d, __uint_as_float(v[c]));
+                            }
+                    }
+                } else if (p.mode == GX_STORE_UPPER) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (j0 + c < p.N) crow[j0 + c] = __uint_as_float(v[c]);
+                } else {
+                    const int cmax = (p.mode == GX_SUB_LOWER) ? min(p.N, r + 1) : p.N;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c)
+                        if (j0 + c < cmax) crow[j0 + c] = __fsub_rn(crow[j0 + c], __uint_as_float(v[c]));
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, GX_TMEM_COLS);
+}
+
+// ---- operand preparation -------------------------------------------------------------------------
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    lo = __fsub_rn(x, hi);
+}
+
+// hi/lo copies of a row-major matrix; optionally transposed on the way (out[c][r] = in[r][c])
+__global__ void __launch_bounds__(256)
+split_kernel(const float* __restrict__ in, int64_t ld_in, int rows, int cols, float* __restrict__ hi,
+             float* __restrict__ lo, int64_t ld_out, int transpose) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    if (!transpose) {
+        for (int i = ty; i < 32; i += 8) {
+            const int r = r0 + i, c = c0 + tx;
+            if (r < rows && c < cols) {
+                float h, l;
+                split_tf32(in[(int64_t)r * ld_in + c], h, l);
+                hi[(int64_t)r * ld_out + c] = h;
+                lo[(int64_t)r * ld_out + c] = l;
+            }
+        }
+        return;
+    }
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + tx;
+        tile[i][tx] = (r < rows && c < cols) ? in[(int64_t)r * ld_in + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + tx;                           // output row = input column
+        if (r < rows && c < cols) {
+            float h, l;
+            split_tf32(tile[tx][i], h, l);
+            hi[(int64_t)c * ld_out + r] = h;
+            lo[(int64_t)c * ld_out + r] = l;
+        }
+    }
+}
+
+// B operand of the error feedback, K-major:  coef[j][i] = Hinv[blk_i, rem_j] / clamp(Hinv[blk_i, blk_i], 1e-8)
+// (gptq.py:173-181), written as hi/lo.  Reads walk rem_j (ascending, near-contiguous) along rows blk_i of Hinv.
+__global__ void __launch_bounds__(256)
+feedback_coef_kernel(const float* __restrict__ Hinv, int64_t ldh, const int32_t* __restrict__ blk_idx, int blk0, int b,
+                     const int32_t* __restrict__ rem_idx, int rem0, int rem, float* __restrict__ hi,
+                     float* __restrict__ lo, int64_t ldb) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
+    for (int ii = ty; ii < 32; ii += 8) {
+        const int i = i0 + ii, j = j0 + tx;
+        float v = 0.f;
+        if (i < b && j < rem) {
+            const int bc = blk_idx ? blk_idx[i] : blk0 + i;
+            const int rc = rem_idx ? rem_idx[j] : rem0 + j;
+            const float* hrow = Hinv + (int64_t)bc * ldh;
+            v = __fdiv_rn(hrow[rc], fmaxf(hrow[bc], kTiny));
+        }
+        tile[ii][tx] = v;
+    }
+    __syncthreads();
+    for (int jj = ty; jj < 32; jj += 8) {
+        const int j = j0 + jj, i = i0 + tx;
+        if (j < rem && i < b) {
+            float h, l;
+            split_tf32(tile[tx][jj], h, l);
+            hi[(int64_t)j * ldb + i] = h;
+            lo[(int64_t)j * ldb + i] = l;
+        }
+    }
+}
+
+int launch_split(const float* in, int64_t ld_in, int64_t rows, int64_t cols, float* hi, float* lo, int64_t ld_out,
+                 int transpose, cudaStream_t st) {
+    dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
+    split_kernel<<<grid, 256, 0, st>>>(in, ld_in, (int)rows, (int)cols, hi, lo, ld_out, transpose);
+    TQ_LAUNCH_CHECK("split_kernel");
+    return 0;
+}
+
+// C (op)= A B' ; A (M x K) and B (N x K) given as hi/lo pairs with leading dimensions lda / ldb (multiples of 4)
+int launch_gemm_tf32x3(int mode, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* Ah, const float* Al,
+                       int64_t lda, const float* Bh, const float* Bl, int64_t ldb, const int32_t* col_idx, int64_t col0,
+                       cudaStream_t st) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    TQ_CHECK_ARG((lda % 4) == 0 && (ldb % 4) == 0, "gemm_tf32x3: operand leading dimensions must be multiples of 4");
+    CUtensorMap mah, mal, mbh, mbl;
+    int rc;
+    if ((rc = make_tmap_2d(&mah, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Ah, M, K, lda, GX_BM, GX_BK, "gemm_tf32x3(A hi)"))) return rc;
+    if ((rc = make_tmap_2d(&mal, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Al, M, K, lda, GX_BM, GX_BK, "gemm_tf32x3(A lo)"))) return rc;
+    if ((rc = make_tmap_2d(&mbh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Bh, N, K, ldb, GX_BN, GX_BK, "gemm_tf32x3(B hi)"))) return rc;
+    if ((rc = make_tmap_2d(&mbl, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Bl, N, K, ldb, GX_BN, GX_BK, "gemm_tf32x3(B lo)"))) return rc;
+    GxProblem p;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K;
+    p.mt = (int)ceil_div(M, GX_BM);
+    p.nt = (int)ceil_div(N, GX_BN);
+    p.mode = mode;
+    p.C = C; p.ldc = ldc; p.col_idx = col_idx; p.col0 = (int)col0;
+    if (mode == GX_SUB_LOWER) {
+        p.tiles = 0;
+        for (int j = 0; j < p.nt; ++j) p.tiles += (p.mt - j > 0) ? p.mt - j : 0;
+    } else if (mode == GX_STORE_UPPER) {
+        p.tiles = 0;
+        for (int j = 0; j < p.nt; ++j) p.tiles += (p.mt < j + 1) ? p.mt : j + 1;
+    } else {
+        p.tiles = p.mt * p.nt;
+    }
+    if (p.tiles <= 0) return 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+        TQ_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GX_SMEM));
+        attr_set = true;
+    }
+    const int sms = sm_count();
+    const int grid = p.tiles < sms ? p.tiles : sms;
+    gemm_tf32x3_kernel<<<grid, GX_THREADS, GX_SMEM, st>>>(mah, mal, mbh, mbl, p);
+    TQ_LAUNCH_CHECK("gemm_tf32x3_kernel");
+    return 0;
+}
+
+// W[:, rem] -= E C on the tensor cores.  E is given as hi/lo [n, lde]; coef_ws holds 2 * rem * ldb floats.
+int launch_err_feedback_tc(float* W, int64_t ldw, int64_t n, const float* Eh, const float* El, int64_t lde,
+                           const float* Hinv, int64_t ldh, const int32_t* blk_idx, int64_t blk0, int64_t b,
+                           const int32_t* rem_idx, int64_t rem0, int64_t rem, float* coef_ws, int64_t ldb,
+                           cudaStream_t st) {
+    if (rem <= 0) return 0;
+    float* ch = coef_ws;
+    float* cl = coef_ws + rem * ldb;
+    dim3 grid((unsigned)ceil_div(rem, 32), (unsigned)ceil_div(b, 32));
+    feedback_coef_kernel<<<grid, 256, 0, st>>>(Hinv, ldh, blk_idx, (int)blk0, (int)b, rem_idx, (int)rem0, (int)rem, ch, cl, ldb);
+    TQ_LAUNCH_CHECK("feedback_coef_kernel");
+    return launch_gemm_tf32x3(GX_FEEDBACK, W, ldw, n, rem, b, Eh, El, lde, ch, cl, ldb, rem_idx, rem0, st);
+}
+
+}  // namespace tq
+
+extern "C" int tq_split_tf32(const float* x, int64_t ld, int64_t rows, int64_t cols, float* hi, float* lo,
+                             int64_t ld_out, void* stream) {
+    using namespace tq;
+    TQ_CHECK_ARG(x && hi && lo && rows > 0 && cols > 0 && ld >= cols && ld_out >= cols, "tq_split_tf32: bad arguments");
+    return launch_split(x, ld, rows, cols, hi, lo, ld_out, 0, (cudaStream_t)stream);
+}
+
+extern "C" int64_t tq_err_feedback_tc_workspace_floats(int64_t n, int64_t b, int64_t rem) {
+    const int64_t ldb = (b + 3) & ~(int64_t)3;
+    return 2 * n * ldb + 2 * rem * ldb;
+}
+
+extern "C" int tq_err_feedback_tc(float* W, int64_t ldw, int64_t n, const float* E, int64_t lde, const float* Hinv,
+                                  int64_t ldh, const int32_t* blk_idx, int64_t blk0, int64_t b, const int32_t* rem_idx,
+                                  int64_t rem0, int64_t rem, float* workspace, void* stream) {
+    using namespace tq;
+    TQ_CHECK_ARG(W && E && Hinv && workspace, "tq_err_feedback_tc: null pointer");
+    TQ_CHECK_ARG(n > 0 && b > 0 && b <= 512 && rem >= 0 && lde >= b, "tq_err_feedback_tc: bad shape");
+    TQ_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "tq_err_feedback_tc: workspace must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t ldb = (b + 3) & ~(int64_t)3;
+    float* eh = workspace;
+    float* el = eh + n * ldb;
+    float* coef = el + n * ldb;
+    int rc;
+    if ((rc = launch_split(E, lde, n, b, eh, el, ldb, 0, st))) return rc;
+    return launch_err_feedback_tc(W, ldw, n, eh, el, ldb, Hinv, ldh, blk_idx, blk0, b, rem_idx, rem0, rem, coef, ldb, st);
+}

@@ -15,9 +15,7 @@
 //               only tiles that touch the upper triangle are computed (tq_symmetrize mirrors later)
 //   roles     : warp 0 TMA producer, warp 1 MMA issuer (one thread), warp 2 TMEM allocator,
 //               warps 4-7 epilogue (TMEM lane quarter = warp % 4)
-#include "common.cuh"
-
-#include <cuda.h>
+#include "tc_common.cuh"
 
 namespace tq {
 
@@ -31,89 +29,6 @@ constexpr int HT_EPI_BYTES = HT_BM * HT_EPI_COLS * 4;      // 16384
 constexpr int HT_EPI_STAGES = 2;
 constexpr int HT_THREADS = 256;
 constexpr int HT_SMEM = HT_STAGES * HT_STAGE_BYTES + HT_EPI_STAGES * HT_EPI_BYTES + 256 + 1024;
-constexpr unsigned long long HT_SPIN_LIMIT = 4000000000ull;  // ~2 s of SM clocks: trap instead of hanging the box
-
-__device__ int g_ht_timeout_flag = 0;
-
-// ---- PTX wrappers ------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const unsigned long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > HT_SPIN_LIMIT) {
-            atomicExch(&g_ht_timeout_flag, 1);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
-    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
-                 ::"l"(map), "r"(src), "r"(c0), "r"(c1)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
-
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // smem matrix descriptor for an MN-major, 128B-swizzled operand slab made of [64 cols x 64 tokens] TMA boxes:
 //   8 token rows x 128 B = one 1024 B swizzle atom; next 8 tokens at +1024 B (SBO); next 64 columns at +8192 B (LBO)
@@ -162,8 +77,7 @@ hessian_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         fence_barrier_init();
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        tmem_alloc_512(smem_u32(tmem_slot));
     }
     tc_fence_before();
     __syncthreads();
@@ -271,16 +185,12 @@ hessian_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        tmem_dealloc_512(tmem_base);
     }
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_tmapEncodeTiled encode_fn() {
+PFN_tmapEncodeTiled tmap_encode_fn() {
     static PFN_tmapEncodeTiled fn = nullptr;
     if (!fn) {
         void* p = nullptr;
@@ -292,42 +202,37 @@ static PFN_tmapEncodeTiled encode_fn() {
     return fn;
 }
 
-int hessian_accum_tcgen05(float* H, int64_t ldh, const void* X, int64_t Nt, int64_t m, int64_t ldx, int dtype,
-                          cudaStream_t st) {
-    PFN_tmapEncodeTiled enc = encode_fn();
+int make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, int64_t rows, int64_t cols,
+                 int64_t ld, int box_rows, int box_cols, const char* what) {
+    PFN_tmapEncodeTiled enc = tmap_encode_fn();
     if (!enc) {
-        set_error("tq_hessian_accum: cuTensorMapEncodeTiled not available from the driver");
+        set_error("%s: cuTensorMapEncodeTiled not available from the driver", what);
         return TQ_E_UNSUPPORTED;
     }
-    TQ_CHECK_ARG(Nt < (1ll << 31) && m < (1ll << 31), "tq_hessian_accum: sizes exceed the TMA coordinate range");
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * (cuuint64_t)elem_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("%s: cuTensorMapEncodeTiled failed with CUresult %d (base %p rows %lld cols %lld ld %lld)", what, (int)r,
+                  base, (long long)rows, (long long)cols, (long long)ld);
+        return TQ_E_BADARG;
+    }
+    return 0;
+}
 
+int hessian_accum_tcgen05(float* H, int64_t ldh, const void* X, int64_t Nt, int64_t m, int64_t ldx, int dtype,
+                          cudaStream_t st) {
+    TQ_CHECK_ARG(Nt < (1ll << 31) && m < (1ll << 31), "tq_hessian_accum: sizes exceed the TMA coordinate range");
     CUtensorMap map_x, map_h;
-    {
-        cuuint64_t dims[2] = {(cuuint64_t)m, (cuuint64_t)Nt};
-        cuuint64_t strides[1] = {(cuuint64_t)ldx * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)HT_BK};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult r = enc(&map_x, dtype == TQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                         const_cast<void*>(X), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            set_error("tq_hessian_accum: cuTensorMapEncodeTiled(X) failed with CUresult %d", (int)r);
-            return TQ_E_BADARG;
-        }
-    }
-    {
-        cuuint64_t dims[2] = {(cuuint64_t)m, (cuuint64_t)m};
-        cuuint64_t strides[1] = {(cuuint64_t)ldh * 4};
-        cuuint32_t box[2] = {(cuuint32_t)HT_EPI_COLS, (cuuint32_t)HT_BM};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult r = enc(&map_h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, H, dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            set_error("tq_hessian_accum: cuTensorMapEncodeTiled(H) failed with CUresult %d", (int)r);
-            return TQ_E_BADARG;
-        }
-    }
+    int rc;
+    if ((rc = make_tmap_2d(&map_x, dtype == TQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, X,
+                           Nt, m, ldx, HT_BK, 64, "tq_hessian_accum(X)")))
+        return rc;
+    if ((rc = make_tmap_2d(&map_h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, H, m, m, ldh, HT_BM, HT_EPI_COLS, "tq_hessian_accum(H)")))
+        return rc;
 
     TileSched sched;
     sched.nbi = (int)ceil_div(m, HT_BM);

@@ -7,7 +7,10 @@
 namespace tq {
 
 int launch_atq_block(const float*, int64_t, int64_t, const int32_t*, int64_t, int64_t, const float*, int, int8_t*,
-                     int64_t, float*, float*, int64_t, float*, int64_t, int32_t*, cudaStream_t);
+                     int64_t, float*, float*, int64_t, float*, float*, int64_t, int32_t*, cudaStream_t);
+int launch_err_feedback_tc(float*, int64_t, int64_t, const float*, const float*, int64_t, const float*, int64_t,
+                           const int32_t*, int64_t, int64_t, const int32_t*, int64_t, int64_t, float*, int64_t,
+                           cudaStream_t);
 int launch_aga_vector(const float*, int64_t, const int32_t*, int64_t, int64_t, int, float*, cudaStream_t);
 int launch_ssr_stats(const float*, int64_t, int64_t, const int32_t*, int64_t, float*, float*, cudaStream_t);
 int launch_ssr_select(const float*, int64_t, const float*, int64_t, const float*, const int32_t*, int64_t, int64_t,
@@ -26,6 +29,8 @@ __global__ void iota_kernel(int32_t* __restrict__ a, int m) {
 
 struct SweepWs {
     float* E;
+    float* E_lo;       // low halves of the tf32 split of E (tensor-core feedback)
+    float* coef;       // [2][m][ldb] hi/lo coefficient operand of the feedback GEMM
     float* rowmean;
     float* partials;
     float* sims;       // [2*m]: similarities + selection keys
@@ -44,7 +49,10 @@ static SweepWs carve(void* base, int64_t n, int64_t m, int64_t block) {
     int64_t off = 0;
     auto take = [&](int64_t bytes) { char* q = p ? p + off : nullptr; off += align256(bytes); return q; };
     const int64_t chunks = tq_ssr_num_chunks(n);
-    w.E = reinterpret_cast<float*>(take(sizeof(float) * n * block));
+    const int64_t ldb = (block + 3) & ~(int64_t)3;
+    w.E = reinterpret_cast<float*>(take(sizeof(float) * n * ldb));
+    w.E_lo = reinterpret_cast<float*>(take(sizeof(float) * n * ldb));
+    w.coef = reinterpret_cast<float*>(take(sizeof(float) * 2 * m * ldb));
     w.rowmean = reinterpret_cast<float*>(take(sizeof(float) * n));
     w.partials = reinterpret_cast<float*>(take(sizeof(float) * chunks * 2 * m));
     w.sims = reinterpret_cast<float*>(take(sizeof(float) * 2 * m));
@@ -87,6 +95,8 @@ extern "C" int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const
     }
     const int64_t nb = ceil_div(m, block);
     const int64_t chunks = tq_ssr_num_chunks(n);
+    const int64_t ldb = (block + 3) & ~(int64_t)3;
+    const bool tc_feedback = (flags & TQ_SWEEP_FFMA_FEEDBACK) == 0;
     const float* Haga = (aga == TQ_AGA_HESSIAN) ? Hd : Hraw;
     int rc;
 
@@ -140,11 +150,15 @@ extern "C" int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const
             s1d = ws.s1d;
         }
         if ((rc = launch_atq_block(W, ldw, n, blk_idx, done, b, s1d, max_iter, ws.Tperm + done, m, alpha + k, mu + k,
-                                   nb, ws.E, block, nullptr, st)))
+                                   nb, ws.E, tc_feedback ? ws.E_lo : nullptr, ldb, nullptr, st)))
             return rc;
         if (rem > 0) {                                            // gptq.py:170 (and SURVEY Q3)
-            if ((rc = launch_err_feedback(W, ldw, n, ws.E, block, Hinv, m, blk_idx, done, b, rem_idx, done + b, rem, st)))
-                return rc;
+            if (tc_feedback)
+                rc = launch_err_feedback_tc(W, ldw, n, ws.E, ws.E_lo, ldb, Hinv, m, blk_idx, done, b, rem_idx, done + b,
+                                            rem, ws.coef, ldb, st);
+            else
+                rc = launch_err_feedback(W, ldw, n, ws.E, ldb, Hinv, m, blk_idx, done, b, rem_idx, done + b, rem, st);
+            if (rc) return rc;
         }
         done += b;
     }

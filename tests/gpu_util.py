@@ -83,3 +83,14 @@ def err_feedback(W, E, Hinv, blk_idx, blk0, b, rem_idx, rem0, rem):
                                  _lib.stream()), "tq_err_feedback")
     torch.cuda.synchronize()
     return W
+
+
+def err_feedback_tc(W, E, Hinv, blk_idx, blk0, b, rem_idx, rem0, rem):
+    L = lib()
+    n = W.shape[0]
+    ws = torch.empty(L.tq_err_feedback_tc_workspace_floats(n, b, rem), dtype=torch.float32, device=DEV)
+    _lib.check(L.tq_err_feedback_tc(_lib.ptr(W), W.stride(0), n, _lib.ptr(E), E.stride(0), _lib.ptr(Hinv),
+                                    Hinv.stride(0), _lib.ptr(blk_idx), blk0, b, _lib.ptr(rem_idx), rem0, rem,
+                                    _lib.ptr(ws), _lib.stream()), "tq_err_feedback_tc")
+    torch.cuda.synchronize()
+    return W

@@ -303,6 +303,36 @@ def test_err_feedback_vs_numpy(G, gather):
     assert np.array_equal(Wd[:, untouched], W[:, untouched])
 
 
+@pytest.mark.parametrize("gather", [False, True])
+@pytest.mark.parametrize("n,m,b", [(300, 1000, 128), (4096, 4096, 128), (257, 777, 72)])
+def test_err_feedback_tensor_core_vs_fp64(G, gather, n, m, b):
+    """3xTF32 tcgen05 feedback GEMM: as close to the exact update as the fp32 CUDA-core kernel is."""
+    rng = np.random.default_rng(n + m + b)
+    W = synth.make_weight(n, m, seed=52)
+    E = (rng.standard_normal((n, b)) * 0.01).astype(np.float32)
+    A = rng.standard_normal((m, 2 * m // 3)).astype(np.float32)
+    Hinv = (A @ A.T / m + np.eye(m, dtype=np.float32)).astype(np.float32)
+    if gather:
+        perm = rng.permutation(m)
+        blk, rem = perm[:b], np.sort(perm[b:])
+    else:
+        blk, rem = np.arange(b, 2 * b), np.arange(2 * b, m)
+    C = (Hinv[np.ix_(blk, rem)] / np.maximum(np.diag(Hinv)[blk], 1e-8)[:, None]).astype(np.float32)
+    upd = E.astype(np.float64) @ C.astype(np.float64)
+    exact = W.astype(np.float64).copy()
+    exact[:, rem] -= upd
+    args = (G.i32(blk) if gather else None, b, b, G.i32(rem) if gather else None, 2 * b, len(rem))
+    W_tc = G.err_feedback_tc(G.dev(W), G.dev(E), G.dev(Hinv), *args).cpu().numpy()
+    W_ff = G.err_feedback(G.dev(W), G.dev(E), G.dev(Hinv), *args).cpu().numpy()
+    untouched = np.setdiff1d(np.arange(m), rem)
+    assert np.array_equal(W_tc[:, untouched], W[:, untouched])
+    scale = np.abs(upd).max()
+    err_tc = np.abs(W_tc - exact).max() / scale
+    err_ff = np.abs(W_ff - exact).max() / scale
+    print(f"feedback error relative to max|update|: tensor-core {err_tc:.3e}, fp32 CUDA cores {err_ff:.3e}")
+    assert err_tc < 4e-6 and err_tc < 8 * max(err_ff, 2e-7)
+
+
 # ------------------------------------------------------------------ codec (bit exact)
 def test_pack_unpack_vs_reference_fixture(G, golden_dir):
     import tq100
