@@ -83,6 +83,50 @@ def main():
                 gq.quantize(**kw)
             best, _ = timed(sw, reps=2)
             rec[name] = best
+        # single-block stage timings at the first block (rem = m - 128)
+        import numpy as np
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import gpu_util as G
+        Wd = W.clone()
+        remv = torch.arange(m, device=DEV, dtype=torch.int32)
+        chunks = lib.tq_ssr_num_chunks(n)
+        rowmean = torch.empty(n, device=DEV)
+        partials = torch.empty((chunks, 2, m), device=DEV)
+        blk = torch.empty(128, device=DEV, dtype=torch.int32)
+        newrem = torch.empty(m, device=DEV, dtype=torch.int32)
+        sims = torch.empty(2 * m, device=DEV)
+        def stats():
+            _lib.check(lib.tq_ssr_stats(_lib.ptr(Wd), m, n, _lib.ptr(remv), m, _lib.ptr(rowmean), _lib.ptr(partials), _lib.stream()), "stats")
+        def select():
+            _lib.check(lib.tq_ssr_select(_lib.ptr(partials), chunks, _lib.ptr(rowmean), n, None, _lib.ptr(remv), m, 128,
+                                         _lib.ptr(blk), _lib.ptr(newrem), _lib.ptr(sims), _lib.stream()), "select")
+        rec["ssr_stats_us"] = timed(stats, reps=5)[0] * 1e3
+        rec["ssr_select_us"] = timed(select, reps=5)[0] * 1e3
+        Hinv = st.damped_inverse(0.01)[1]
+        E = torch.randn((n, 128), device=DEV) * 0.01
+        ws = torch.empty(lib.tq_err_feedback_tc_workspace_floats(n, 128, m - 128), device=DEV)
+        rem_g = newrem[: m - 128]
+        def fb_seq():
+            _lib.check(lib.tq_err_feedback_tc(_lib.ptr(Wd), m, n, _lib.ptr(E), 128, _lib.ptr(Hinv), m, None, 0, 128, None, 128,
+                                              m - 128, _lib.ptr(ws), _lib.stream()), "fb")
+        def fb_gather():
+            _lib.check(lib.tq_err_feedback_tc(_lib.ptr(Wd), m, n, _lib.ptr(E), 128, _lib.ptr(Hinv), m, _lib.ptr(blk), 0, 128,
+                                              _lib.ptr(rem_g), 0, m - 128, _lib.ptr(ws), _lib.stream()), "fb")
+        def fb_ffma():
+            _lib.check(lib.tq_err_feedback(_lib.ptr(Wd), m, n, _lib.ptr(E), 128, _lib.ptr(Hinv), m, None, 0, 128, None, 128,
+                                           m - 128, _lib.stream()), "fb")
+        rec["feedback_tc_seq_us"] = timed(fb_seq, reps=5)[0] * 1e3
+        rec["feedback_tc_gather_us"] = timed(fb_gather, reps=5)[0] * 1e3
+        rec["feedback_ffma_seq_us"] = timed(fb_ffma, reps=3)[0] * 1e3
+        rec["feedback_rmw_bytes"] = 8 * n * (m - 128)
+        rec["feedback_tc_seq_gbs"] = rec["feedback_rmw_bytes"] / rec["feedback_tc_seq_us"] / 1e3
+        T8 = torch.empty((n, 128), device=DEV, dtype=torch.int8); al = torch.empty(n, device=DEV); mu_ = torch.empty(n, device=DEV)
+        Eo = torch.empty((n, 128), device=DEV)
+        def atq():
+            _lib.check(lib.tq_atq_block(_lib.ptr(Wd), m, n, _lib.ptr(blk), 0, 128, None, 100, _lib.ptr(T8), 128, _lib.ptr(al),
+                                        _lib.ptr(mu_), 1, _lib.ptr(Eo), 128, None, _lib.stream()), "atq")
+        rec["atq_block_gather_us"] = timed(atq, reps=5)[0] * 1e3
+        del Wd, partials, ws, E
         out.append(rec)
         print(json.dumps(rec))
         del X, W, H, st, gq

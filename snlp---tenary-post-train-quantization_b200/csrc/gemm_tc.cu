@@ -17,13 +17,17 @@
 //   8 bytes per element per call at K = 128, i.e. HBM-bound -- SURVEY 8d)
 #include "tc_common.cuh"
 
+#include <stdlib.h>
+
 namespace tq {
 
-constexpr int GX_BM = 128, GX_BN = 128, GX_BK = 32, GX_STAGES = 3, GX_UMMA_K = 8;
+constexpr int GX_BM = 128, GX_BN = 128, GX_BK = 32, GX_STAGES = 2, GX_UMMA_K = 8;
 constexpr int GX_SLAB = GX_BM * GX_BK * 4;            // 16384
 constexpr int GX_STAGE_BYTES = 4 * GX_SLAB;           // 65536
-constexpr int GX_THREADS = 256;
-constexpr int GX_SMEM = GX_STAGES * GX_STAGE_BYTES + 256 + 1024;
+constexpr int GX_THREADS = 384;                 // 4 control warps + 8 epilogue warps
+constexpr int GX_EPI_WARPS = 8;
+constexpr int GX_CT_LD = GX_BN + 1;                // pitch of the C tile in shared memory (bank-conflict-free both ways)
+constexpr int GX_SMEM = GX_STAGES * GX_STAGE_BYTES + 256 + GX_BM * GX_CT_LD * 4 + 1024;   // stages, barriers, C tile, slack   // stages, barriers, epilogue staging, alignment slack
 constexpr int GX_TMEM_COLS = 256;
 
 enum GxMode {
@@ -41,6 +45,7 @@ struct GxProblem {
     int64_t ldc;
     const int32_t* col_idx; // FEEDBACK: absolute column of remaining position j (NULL: col0 + j)
     int col0;
+    int debug;              // development switch (env TQ_GX_DEBUG): 1 = drain accumulators only, 2 = no prefetch loads
 };
 
 __device__ __forceinline__ void gx_decode(const GxProblem& p, int t, int& bi, int& bj) {
@@ -96,7 +101,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < GX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), GX_EPI_WARPS * 32); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(smem_u32(tmem_slot), GX_TMEM_COLS);
@@ -159,68 +164,85 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: TMEM -> registers -> global read-modify-write =====
+        // ===== epilogue: read-modify-write of the C tile through shared memory.
+        // Eight warps; warp % 4 is the TMEM lane quarter (32 rows), (warp - 4) / 4 the half of the tile's columns.
+        //  1. BEFORE the accumulator is awaited, the old values of the warp's 32 x 64 block of C are fetched with
+        //     cp.async straight into a padded smem tile: no registers, 64 independent 128-byte row segments in
+        //     flight per warp (64 KB per SM) while this tile's MMAs run.  Lanes run along the columns, so every
+        //     request is one row segment of 32 consecutive (with SSR: ascending, near-consecutive) columns.
+        //  2. tcgen05.ld hands each thread one ROW of accumulators; it subtracts them from its row of the smem
+        //     tile (pitch 129: conflict-free).
+        //  3. The warp walks its block row by row, lanes along the columns again, and stores coalesced.
         const int q = warp & 3;
-        const int row = q * 32 + lane;
+        const int half = (warp - 4) >> 2;
+        constexpr int NCG = GX_BN / 64;                          // column groups of 32 per warp
+        float* ctile = reinterpret_cast<float*>(smem + GX_STAGES * GX_STAGE_BYTES + 256);
+        float* cw = ctile + (q * 32) * GX_CT_LD + half * 64;    // this warp's 32 x 64 block
+        const bool rmw = (p.mode != GX_STORE_UPPER) && p.debug != 2;
+        const bool lower = (p.mode == GX_SUB_LOWER);
         int n_item = 0;
         for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++n_item) {
             int bi, bj;
             gx_decode(p, t, bi, bj);
+            const int r0 = bi * GX_BM + q * 32;                  // first row of this warp's block
+            const int rows = min(32, p.M - r0);                  // <= 0 on a ragged last row tile
+            int col[NCG];
+#pragma unroll
+            for (int cg = 0; cg < NCG; ++cg) {
+                const int j = bj * GX_BN + half * 64 + cg * 32 + lane;      // this lane's position in the N range
+                col[cg] = -1;
+                if (j < p.N) col[cg] = (p.mode == GX_FEEDBACK) ? (p.col_idx ? p.col_idx[j] : p.col0 + j) : j;
+            }
+            if (rmw) {
+#pragma unroll
+                for (int cg = 0; cg < NCG; ++cg) {
+                    if (col[cg] >= 0) {
+                        const float* src = p.C + (int64_t)r0 * p.ldc + col[cg];
+                        const uint32_t dst = smem_u32(cw + cg * 32 + lane);
+#pragma unroll 8
+                        for (int rr = 0; rr < rows; ++rr)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + rr * GX_CT_LD * 4),
+                                         "l"(src + (int64_t)rr * p.ldc)
+                                         : "memory");
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
             const int acc = n_item & 1;
             mbar_wait(tfull_bar(acc), (n_item >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * GX_BN;
-            const int r = bi * GX_BM + row;
-            float* crow = p.C + (int64_t)r * p.ldc;
-            for (int cg = 0; cg < GX_BN / 32; ++cg) {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncwarp();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * GX_BN + half * 64;
+            float* myrow = cw + lane * GX_CT_LD;
+#pragma unroll
+            for (int cg = 0; cg < NCG; ++cg) {
                 uint32_t v[32];
                 tmem_ld_32x32(taddr + cg * 32, v);
                 tmem_ld_wait();
-                if (cg == GX_BN / 32 - 1) {
+                if (cg == NCG - 1) {
                     tc_fence_before();
                     mbar_arrive(tempty_bar(acc));
                 }
-                const int j0 = bj * GX_BN + cg * 32;
-                if (r >= p.M || j0 >= p.N) continue;
-                if (p.mode == GX_FEEDBACK) {
-                    if (p.col_idx == nullptr) {
-                        const int c0 = p.col0 + j0;
-                        if (j0 + 32 <= p.N && ((c0 & 3) == 0) && ((p.ldc & 3) == 0) &&
-                            ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0)) {
-                            float4* dst = reinterpret_cast<float4*>(crow + c0);
 #pragma unroll
-                            for (int c = 0; c < 8; ++c) {
-                                float4 w = dst[c];
-                                w.x = __fsub_rn(w.x, __uint_as_float(v[4 * c]));
-                                w.y = __fsub_rn(w.y, __uint_as_float(v[4 * c + 1]));
-                                w.z = __fsub_rn(w.z, __uint_as_float(v[4 * c + 2]));
-                                w.w = __fsub_rn(w.w, __uint_as_float(v[4 * c + 3]));
-                                dst[c] = w;
-                            }
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < 32; ++c)
-                                if (j0 + c < p.N) crow[c0 + c] = __fsub_rn(crow[c0 + c], __uint_as_float(v[c]));
-                        }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 32; ++c)
-                            if (j0 + c < p.N) {
-                                float* d = crow + p.col_idx[j0 + c];
-                                *d = __fsub_rn(*d, __uint_as_float(v[c]));
-                            }
-                    }
-                } else if (p.mode == GX_STORE_UPPER) {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c)
-                        if (j0 + c < p.N) crow[j0 + c] = __uint_as_float(v[c]);
-                } else {
-                    const int cmax = (p.mode == GX_SUB_LOWER) ? min(p.N, r + 1) : p.N;
-#pragma unroll
-                    for (int c = 0; c < 32; ++c)
-                        if (j0 + c < cmax) crow[j0 + c] = __fsub_rn(crow[j0 + c], __uint_as_float(v[c]));
+                for (int c = 0; c < 32; ++c) {
+                    const float a = __uint_as_float(v[c]);
+                    myrow[cg * 32 + c] = rmw ? __fsub_rn(myrow[cg * 32 + c], a) : a;
                 }
             }
+            __syncwarp();
+            if (p.debug != 1) {
+#pragma unroll
+                for (int cg = 0; cg < NCG; ++cg) {
+                    if (col[cg] >= 0) {
+                        float* dstp = p.C + (int64_t)r0 * p.ldc + col[cg];
+#pragma unroll 8
+                        for (int rr = 0; rr < rows; ++rr)
+                            if (!lower || col[cg] <= r0 + rr) dstp[(int64_t)rr * p.ldc] = cw[rr * GX_CT_LD + cg * 32 + lane];
+                    }
+                }
+            }
+            __syncwarp();
         }
     }
 
@@ -328,6 +350,7 @@ int launch_gemm_tf32x3(int mode, float* C, int64_t ldc, int64_t M, int64_t N, in
     p.nt = (int)ceil_div(N, GX_BN);
     p.mode = mode;
     p.C = C; p.ldc = ldc; p.col_idx = col_idx; p.col0 = (int)col0;
+    { const char* e = getenv("TQ_GX_DEBUG"); p.debug = e ? atoi(e) : 0; }
     if (mode == GX_SUB_LOWER) {
         p.tiles = 0;
         for (int j = 0; j < p.nt; ++j) p.tiles += (p.mt - j > 0) ? p.mt - j : 0;
