@@ -137,10 +137,10 @@ int tq_err_feedback(float* W, int64_t ldw, int64_t n, const float* E, int64_t ld
                     const float* Hinv, int64_t ldh, const int32_t* blk_idx, int64_t blk0, int64_t b,
                     const int32_t* rem_idx, int64_t rem0, int64_t rem, void* stream);
 
-/* Tensor-core form of the same update: E C as a 3xTF32 tcgen05 GEMM (hi*hi' + hi*lo' + lo*hi', fp32
- * accumulate in TMEM), fp32-faithful to ~2^-21 relative per product.  workspace:
+/* Tensor-core form of the same update: E C as a split-TF32 tcgen05 GEMM (lo*lo' + lo*hi' + hi*lo' + hi*hi',
+ * fp32 accumulate in TMEM), ~2^-22 relative per product.  workspace:
  * tq_err_feedback_tc_workspace_floats(n, b, rem) floats, 16-byte aligned.  tq_split_tf32 writes the
- * (hi, lo) split of a row-major matrix (hi = low 13 mantissa bits cleared, lo = x - hi). */
+ * (hi, lo) split of a row-major matrix (hi = rn_tf32(x), lo = rn_tf32(x - hi)). */
 int64_t tq_err_feedback_tc_workspace_floats(int64_t n, int64_t b, int64_t rem);
 int tq_err_feedback_tc(float* W, int64_t ldw, int64_t n, const float* E, int64_t lde,
                        const float* Hinv, int64_t ldh, const int32_t* blk_idx, int64_t blk0, int64_t b,

@@ -158,7 +158,7 @@ struct Row {
     }
 
     // gptq.py:158-159.  With erow_lo the error is written as the (hi, lo) tf32 split the tensor-core feedback
-    // GEMM consumes (hi = low 13 mantissa bits cleared, lo = e - hi, both exact), else as plain fp32.
+    // GEMM consumes (hi = rn_tf32(e), lo = rn_tf32(e - hi)), else as plain fp32.
     __device__ __forceinline__ void store_error(float* __restrict__ erow, float* __restrict__ erow_lo, int b, float alpha,
                                                 float mu, bool vec_ok) const {
         float ev[EPL], el[EPL];
@@ -167,8 +167,11 @@ struct Row {
             ev[e] = __fsub_rn(w[e], __fadd_rn(__fmul_rn(alpha, (float)t[e]), mu));
             el[e] = 0.f;
             if (erow_lo != nullptr) {
-                const float hi = __uint_as_float(__float_as_uint(ev[e]) & 0xFFFFE000u);
-                el[e] = __fsub_rn(ev[e], hi);
+                uint32_t hb, lb;                         // hi = rn_tf32(e), lo = rn_tf32(e - hi)  (gemm_tc.cu)
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(ev[e]));
+                const float hi = __uint_as_float(hb);
+                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(__fsub_rn(ev[e], hi)));
+                el[e] = __uint_as_float(lb);
                 ev[e] = hi;
             }
         }

@@ -10,9 +10,14 @@
 //                                 X_k,: = D_k R_k,:                           (trtri_row_kernel)
 //                                 R_i,: -= L_ik X_k,:         for i > k       (trtri_update_kernel)
 //   3. lauum : Hinv = X'X (upper tiles, K range starts at the tile's column), then mirrored.
+// By default the three bulk updates (chol_syrk, trtri_update, lauum: all of the O(m^3) work) run on the
+// tensor cores through the 3xTF32 GEMM of gemm_tc.cu, fed with (hi, lo) splits of the panels; the fp32
+// CUDA-core kernels below remain as the reference path (environment TQ_CHOL_FFMA=1).
 // A non-positive pivot is reported through *info (1-based index, LAPACK convention); the caller takes
 // the reference's pinv route (gptq.py:104-106).
 #include "gemm_simt.cuh"
+
+#include <stdlib.h>
 
 namespace tq {
 
@@ -289,11 +294,22 @@ lauum_kernel(float* __restrict__ Hinv, int64_t ldh, const float* __restrict__ X,
     }
 }
 
+int launch_split(const float*, int64_t, int64_t, int64_t, float*, float*, int64_t, int, cudaStream_t);     // gemm_tc.cu
+int launch_gemm_tf32x3(int, float*, int64_t, int64_t, int64_t, int64_t, const float*, const float*, int64_t, const float*,
+                       const float*, int64_t, const int32_t*, int64_t, cudaStream_t);
+enum { GXM_SUB_LOWER = 1, GXM_SUB_RECT = 2, GXM_STORE_UPPER = 3 };   // GxMode of gemm_tc.cu
+
+static inline int64_t chol_split_floats(int64_t m) {
+    const int64_t mp = ceil_div(m, CB) * CB;
+    const int64_t a = 2 * m * m, b = 4 * mp * CB;
+    return a > b ? a : b;
+}
+
 }  // namespace tq
 
 extern "C" int64_t tq_chol_workspace_floats(int64_t m) {
     const int64_t panels = tq::ceil_div(m, tq::CB);
-    return m * m + panels * tq::CB * tq::CB;
+    return m * m + panels * tq::CB * tq::CB + tq::chol_split_floats(m);
 }
 
 extern "C" int tq_chol_inverse(float* Hinv, const float* Hd, int64_t m, float* work, int* info_dev, void* stream) {
@@ -307,6 +323,13 @@ extern "C" int tq_chol_inverse(float* Hinv, const float* Hd, int64_t m, float* w
     float* X = work;                       // L^-1
     float* D = work + m * m;               // per-panel inverses of the diagonal blocks
     const int panels = (int)ceil_div(m, CB);
+    float* S = D + (int64_t)panels * CB * CB;          // (hi, lo) operand splits for the tensor-core updates
+    const int64_t mp = (int64_t)panels * CB;
+    float *Ph = S, *Pl = S + mp * CB, *Bh = S + 2 * mp * CB, *Bl = S + 3 * mp * CB;   // panel / strip operands, ld = CB
+    // TQ_CHOL_FFMA bit mask selects the fp32 CUDA-core kernel per phase: 1 = potrf update, 2 = trtri update, 4 = lauum
+    static const int ffma_mask = []() { const char* e = getenv("TQ_CHOL_FFMA"); return e ? atoi(e) : 0; }();
+    const bool tc_potrf = !(ffma_mask & 1), tc_trtri = !(ffma_mask & 2), tc_lauum = !(ffma_mask & 4);
+    int rc;
 
     static bool attr_set = false;
     const int diag_smem = (2 * CB * CB_LD + 3 * SB * (SB + 1)) * (int)sizeof(float);
@@ -331,8 +354,16 @@ extern "C" int tq_chol_inverse(float* Hinv, const float* Hd, int64_t m, float* w
             const int tiles = (int)ceil_div(below, GT_M);
             chol_trsm_kernel<<<tiles, GT_THREADS, 0, st>>>(L, ld, M, k0, Dk);
             TQ_LAUNCH_CHECK("chol_trsm_kernel");
-            chol_syrk_kernel<<<dim3(tiles, tiles), GT_THREADS, 0, st>>>(L, ld, M, k0);
-            TQ_LAUNCH_CHECK("chol_syrk_kernel");
+            if (tc_potrf) {
+                // A_ij -= L_ik L_jk' on the tensor cores: both operands are the freshly solved panel
+                if ((rc = launch_split(L + (int64_t)(k0 + CB) * ld + k0, ld, below, CB, Ph, Pl, CB, 0, st))) return rc;
+                if ((rc = launch_gemm_tf32x3(GXM_SUB_LOWER, L + (int64_t)(k0 + CB) * ld + (k0 + CB), ld, below, below, CB,
+                                             Ph, Pl, CB, Ph, Pl, CB, nullptr, 0, st)))
+                    return rc;
+            } else {
+                chol_syrk_kernel<<<dim3(tiles, tiles), GT_THREADS, 0, st>>>(L, ld, M, k0);
+                TQ_LAUNCH_CHECK("chol_syrk_kernel");
+            }
         }
     }
     // phase 2: X = L^-1
@@ -345,12 +376,28 @@ extern "C" int tq_chol_inverse(float* Hinv, const float* Hd, int64_t m, float* w
         TQ_LAUNCH_CHECK("trtri_row_kernel");
         const int below = M - k0 - CB;
         if (below > 0) {
-            trtri_update_kernel<<<dim3(ctiles, (unsigned)ceil_div(below, GT_M)), GT_THREADS, 0, st>>>(X, ld, L, ld, M, k0);
-            TQ_LAUNCH_CHECK("trtri_update_kernel");
+            if (tc_trtri) {
+                // R_i,: -= L_ik X_k,: : A = L panel rows, B = the just-finished strip X_k,: transposed to K-major
+                const int64_t cend = k0 + nb;
+                if ((rc = launch_split(L + (int64_t)(k0 + CB) * ld + k0, ld, below, CB, Ph, Pl, CB, 0, st))) return rc;
+                if ((rc = launch_split(X + (int64_t)k0 * ld, ld, nb, cend, Bh, Bl, CB, 1, st))) return rc;
+                if ((rc = launch_gemm_tf32x3(GXM_SUB_RECT, X + (int64_t)(k0 + CB) * ld, ld, below, cend, nb, Ph, Pl, CB, Bh, Bl,
+                                             CB, nullptr, 0, st)))
+                    return rc;
+            } else {
+                trtri_update_kernel<<<dim3(ctiles, (unsigned)ceil_div(below, GT_M)), GT_THREADS, 0, st>>>(X, ld, L, ld, M, k0);
+                TQ_LAUNCH_CHECK("trtri_update_kernel");
+            }
         }
     }
     // phase 3: Hinv = X'X (upper), then mirror
-    {
+    if (tc_lauum && (m % 4) == 0) {
+        // Y = X' (upper triangular), Hinv = Y Y': rows of Y are K-major operands; the K range of tile (i, j <= ... )
+        // starts at the tile's first column because Y[i][q] = 0 for q < i
+        float *Yh = S, *Yl = S + m * m;
+        if ((rc = launch_split(X, ld, m, m, Yh, Yl, m, 1, st))) return rc;
+        if ((rc = launch_gemm_tf32x3(GXM_STORE_UPPER, Hinv, ld, m, m, m, Yh, Yl, m, Yh, Yl, m, nullptr, 0, st))) return rc;
+    } else {
         const int nt = (int)ceil_div(m, GT_M);
         lauum_kernel<<<dim3(nt, nt), GT_THREADS, 0, st>>>(Hinv, ld, X, ld, M);
         TQ_LAUNCH_CHECK("lauum_kernel");

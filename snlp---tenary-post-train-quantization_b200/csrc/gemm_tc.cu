@@ -1,11 +1,11 @@
 // fp32-faithful tensor-core GEMM for the fp32 stages:  C (op)= A B'  with A [M, K] and B [N, K] both K-major fp32.
 //
 // tcgen05 has no fp32 MMA; kind::tf32 keeps 11 significant bits of each operand.  Every operand is therefore
-// supplied as a (hi, lo) pair prepared by the producing kernel:  hi = x with the low 13 mantissa bits cleared
-// (exactly representable in tf32), lo = x - hi (exact in fp32), and three MMAs accumulate
-//     hi*hi' + hi*lo' + lo*hi'     in fp32 in TMEM
-// (the dropped lo*lo' term and the tf32 rounding of lo are O(2^-22) relative -- fp32 FFMA class; measured
-// against the fp32 CUDA-core kernels in tests/).  Used by
+// supplied as a (hi, lo) pair prepared by the producing kernel:  hi = rn_tf32(x), lo = rn_tf32(x - hi), both
+// exactly representable in tf32 (|x - hi - lo| <= 2^-23 |x|), and four MMAs accumulate
+//     lo*lo' + lo*hi' + hi*lo' + hi*hi'     in fp32 in TMEM
+// so each product carries ~2^-22 relative error (fp32 FFMA: 2^-24); measured against the fp32 CUDA-core
+// kernels in tests/.  The kernel is bound by the read-modify-write of C, not by the MMAs.  Used by
 //   error feedback (gptq.py:173-186)     W[:, rem] -= E C,  A = E, B = C' (built by feedback_coef_kernel)
 //   potrf trailing update                A_ij -= L_ik L_jk'
 //   trtri update                         R_i,: -= L_ik X_k,:
@@ -45,6 +45,8 @@ struct GxProblem {
     int64_t ldc;
     const int32_t* col_idx; // FEEDBACK: absolute column of remaining position j (NULL: col0 + j)
     int col0;
+    int k_chunk;            // > 0: TMEM accumulates at most k_chunk of K at a time; chunks are summed in the
+                            // smem C tile with round-to-nearest fp32 adds (the tensor core's accumulate truncates)
     int debug;              // development switch (env TQ_GX_DEBUG): 1 = drain accumulators only, 2 = no prefetch loads
 };
 
@@ -133,34 +135,39 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
             }
         }
     } else if (warp == 1 && lane == 0) {
-        // ===== MMA issuer: hi*hi' + hi*lo' + lo*hi' =====
+        // ===== MMA issuer: lo*lo' + lo*hi' + hi*lo' + hi*hi' =====
         int stage = 0, phase = 0, n_item = 0;
-        for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++n_item) {
+        for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
             int bi, bj;
             gx_decode(p, t, bi, bj);
-            const int acc = n_item & 1;
-            mbar_wait(tempty_bar(acc), ((n_item >> 1) & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + acc * GX_BN;
             const int kb0 = k_begin_of(bj);
-            bool first = true;
-            for (int k = kb0; k < p.K; k += GX_BK) {
-                mbar_wait(full_bar(stage), phase);
+            const int kc = (p.k_chunk > 0) ? p.k_chunk : p.K;
+            for (int c0 = kb0; c0 < p.K; c0 += kc, ++n_item) {
+                const int c1 = min(p.K, c0 + kc);
+                const int acc = n_item & 1;
+                mbar_wait(tempty_bar(acc), ((n_item >> 1) & 1) ^ 1);
                 tc_fence_after();
-                const uint32_t s0 = s_base + stage * GX_STAGE_BYTES;
+                const uint32_t tmem_d = tmem_base + acc * GX_BN;
+                bool first = true;
+                for (int k = c0; k < c1; k += GX_BK) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t s0 = s_base + stage * GX_STAGE_BYTES;
 #pragma unroll
-                for (int kk = 0; kk < GX_BK / GX_UMMA_K; ++kk) {
-                    const uint32_t off = kk * GX_UMMA_K * 4;                 // 32 bytes along K inside the swizzled row
-                    const uint64_t ah = gx_desc(s0 + 0 * GX_SLAB + off), al = gx_desc(s0 + 1 * GX_SLAB + off);
-                    const uint64_t bh = gx_desc(s0 + 2 * GX_SLAB + off), bl = gx_desc(s0 + 3 * GX_SLAB + off);
-                    umma_tf32(tmem_d, al, bh, idesc, first ? 0u : 1u);
-                    first = false;
-                    umma_tf32(tmem_d, ah, bl, idesc, 1u);
-                    umma_tf32(tmem_d, ah, bh, idesc, 1u);
+                    for (int kk = 0; kk < GX_BK / GX_UMMA_K; ++kk) {
+                        const uint32_t off = kk * GX_UMMA_K * 4;             // 32 bytes along K inside the swizzled row
+                        const uint64_t ah = gx_desc(s0 + 0 * GX_SLAB + off), al = gx_desc(s0 + 1 * GX_SLAB + off);
+                        const uint64_t bh = gx_desc(s0 + 2 * GX_SLAB + off), bl = gx_desc(s0 + 3 * GX_SLAB + off);
+                        umma_tf32(tmem_d, al, bl, idesc, first ? 0u : 1u);     // smallest term first
+                        first = false;
+                        umma_tf32(tmem_d, al, bh, idesc, 1u);
+                        umma_tf32(tmem_d, ah, bl, idesc, 1u);
+                        umma_tf32(tmem_d, ah, bh, idesc, 1u);
+                    }
+                    umma_commit(empty_bar(stage));
+                    if (k + GX_BK >= c1) umma_commit(tfull_bar(acc));
+                    if (++stage == GX_STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(empty_bar(stage));
-                if (k + GX_BK >= p.K) umma_commit(tfull_bar(acc));
-                if (++stage == GX_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
@@ -181,7 +188,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
         const bool rmw = (p.mode != GX_STORE_UPPER) && p.debug != 2;
         const bool lower = (p.mode == GX_SUB_LOWER);
         int n_item = 0;
-        for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++n_item) {
+        for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
             int bi, bj;
             gx_decode(p, t, bi, bj);
             const int r0 = bi * GX_BM + q * 32;                  // first row of this warp's block
@@ -208,27 +215,37 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
                 }
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
-            const int acc = n_item & 1;
-            mbar_wait(tfull_bar(acc), (n_item >> 1) & 1);
-            tc_fence_after();
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-            __syncwarp();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * GX_BN + half * 64;
             float* myrow = cw + lane * GX_CT_LD;
-#pragma unroll
-            for (int cg = 0; cg < NCG; ++cg) {
-                uint32_t v[32];
-                tmem_ld_32x32(taddr + cg * 32, v);
-                tmem_ld_wait();
-                if (cg == NCG - 1) {
-                    tc_fence_before();
-                    mbar_arrive(tempty_bar(acc));
+            const int kb0 = k_begin_of(bj);
+            const int kc = (p.k_chunk > 0) ? p.k_chunk : p.K;
+            bool first_chunk = true;
+            for (int c0 = kb0; c0 < p.K; c0 += kc, ++n_item) {
+                const int acc = n_item & 1;
+                mbar_wait(tfull_bar(acc), (n_item >> 1) & 1);
+                tc_fence_after();
+                if (first_chunk) {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    __syncwarp();
                 }
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * GX_BN + half * 64;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const float a = __uint_as_float(v[c]);
-                    myrow[cg * 32 + c] = rmw ? __fsub_rn(myrow[cg * 32 + c], a) : a;
+                for (int cg = 0; cg < NCG; ++cg) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr + cg * 32, v);
+                    tmem_ld_wait();
+                    if (cg == NCG - 1) {
+                        tc_fence_before();
+                        mbar_arrive(tempty_bar(acc));
+                    }
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const float a = __uint_as_float(v[c]);
+                        const float cur = myrow[cg * 32 + c];
+                        // RMW modes subtract every chunk from the fetched C; STORE mode sums the chunks
+                        myrow[cg * 32 + c] = rmw ? __fsub_rn(cur, a) : (first_chunk ? a : __fadd_rn(cur, a));
+                    }
                 }
+                first_chunk = false;
             }
             __syncwarp();
             if (p.debug != 1) {
@@ -252,9 +269,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
 }
 
 // ---- operand preparation -------------------------------------------------------------------------
+// x = hi + lo' + delta with hi = rn_tf32(x) (11 significant bits), lo' = rn_tf32(x - hi); both are exactly
+// representable in tf32, so the tensor core's own operand conversion is exact, and |delta| <= 2^-23 |x|.
+__device__ __forceinline__ float rn_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-    hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-    lo = __fsub_rn(x, hi);
+    hi = rn_tf32(x);
+    lo = rn_tf32(__fsub_rn(x, hi));
 }
 
 // hi/lo copies of a row-major matrix; optionally transposed on the way (out[c][r] = in[r][c])
@@ -350,6 +374,7 @@ int launch_gemm_tf32x3(int mode, float* C, int64_t ldc, int64_t M, int64_t N, in
     p.nt = (int)ceil_div(N, GX_BN);
     p.mode = mode;
     p.C = C; p.ldc = ldc; p.col_idx = col_idx; p.col0 = (int)col0;
+    p.k_chunk = (mode == GX_STORE_UPPER) ? 256 : 0;
     { const char* e = getenv("TQ_GX_DEBUG"); p.debug = e ? atoi(e) : 0; }
     if (mode == GX_SUB_LOWER) {
         p.tiles = 0;
