@@ -170,7 +170,7 @@ def workload_config(args, reference=False):
             "baseline_config": "configs[1]", "order": "ssr", "aga": "hessian", "block_size": 128,
             "activations": "fp16, one layer's 4 distinct inputs (12.2 GB) reused for all 32 layers",
             "cache": "inputs (12.2 GB activations + 25.9 GB weights) far exceed the 126 MB L2; no explicit flush",
-            "hessians_per_layer": 7, "parallelism": "1 GPU" if args.gpus == 1 else f"{args.gpus} GPUs: "
+            "hessians_per_layer": 7, "streams": args.streams, "parallelism": "1 GPU" if args.gpus == 1 else f"{args.gpus} GPUs: "
             "Hessian sample-sharded + NCCL allreduce, sweep row-sharded, H^-1 replicated"}
 
 
@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=LLAMA2_7B["layers"], help="(debug) fewer layers; the line says so")
+    ap.add_argument("--streams", type=int, default=4, help="CUDA streams the per-linear prologue+sweep chains are spread over")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -241,6 +242,8 @@ def main():
     if world > 1:
         par.init_comm(ctx)
     sharded_layer = par.ShardedLayer(ctx, block_size=128, percdamp=0.01)
+    from tq100.pipeline import LayerDriver
+    driver = LayerDriver(dev, block_size=128, percdamp=0.01, num_streams=args.streams)
 
     def quantize_model(record=False):
         for li in range(cfg["layers"]):
@@ -250,18 +253,18 @@ def main():
                     [(name, weights[li][name], acts[src]) for name, n, m, src in lins], use_ssr=True,
                     hess_timing=hess_events if record else None)
                 continue
-            for name, n, m, src in lins:
-                layer = LinearView(weights[li][name])
-                g = par.ShardedGPTQ(layer, ctx, block_size=128, percdamp=0.01)
-                if record:
-                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    e0.record()
-                g.add_batch(acts[src])
-                if record:
-                    e1.record()
-                    hess_events.append((e0, e1, acts[src].shape[0] * SEQ, m))
-                out = g.quantize(use_ssr=True)
-                results_keep["last"] = out
+            if os.environ.get("BENCH_DEBUG"):
+                torch.cuda.synchronize()
+                t_dbg = time.perf_counter()
+            results_keep["last"] = driver.quantize(
+                [(name, weights[li][name], acts[src]) for name, n, m, src in lins], use_ssr=True,
+                hess_timing=hess_events if record else None)
+            if os.environ.get("BENCH_DEBUG"):
+                torch.cuda.synchronize()
+                print(f"[debug] layer {li}: {1e3 * (time.perf_counter() - t_dbg):.1f} ms, allocated "
+                      f"{torch.cuda.memory_allocated() / 1e9:.1f} GB, reserved {torch.cuda.memory_reserved() / 1e9:.1f} GB, "
+                      f"mallocs {torch.cuda.memory_stats().get('num_device_alloc', -1)}, "
+                      f"frees {torch.cuda.memory_stats().get('num_device_free', -1)}", file=sys.stderr, flush=True)
 
     def barrier():
         if world > 1:
@@ -272,7 +275,7 @@ def main():
         quantize_model()
     barrier()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER"):
         sampler.start()
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

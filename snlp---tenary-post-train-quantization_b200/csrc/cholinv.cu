@@ -17,6 +17,7 @@
 // the reference's pinv route (gptq.py:104-106).
 #include "gemm_simt.cuh"
 
+#include <cuda.h>
 #include <stdlib.h>
 
 namespace tq {
@@ -297,6 +298,13 @@ lauum_kernel(float* __restrict__ Hinv, int64_t ldh, const float* __restrict__ X,
 int launch_split(const float*, int64_t, int64_t, int64_t, float*, float*, int64_t, int, cudaStream_t);     // gemm_tc.cu
 int launch_gemm_tf32x3(int, float*, int64_t, int64_t, int64_t, int64_t, const float*, const float*, int64_t, const float*,
                        const float*, int64_t, const int32_t*, int64_t, cudaStream_t);
+struct GemmOperands {
+    CUtensorMap ah, al, bh, bl;
+    int64_t K;
+};
+int gemm_operands_encode(GemmOperands*, const float*, const float*, int64_t, int64_t, const float*, const float*, int64_t,
+                         int64_t, int64_t);
+int launch_gemm_tf32x3_ops(int, float*, int64_t, int64_t, int64_t, const GemmOperands*, const int32_t*, int64_t, cudaStream_t);
 enum { GXM_SUB_LOWER = 1, GXM_SUB_RECT = 2, GXM_STORE_UPPER = 3 };   // GxMode of gemm_tc.cu
 
 static inline int64_t chol_split_floats(int64_t m) {
@@ -330,6 +338,12 @@ extern "C" int tq_chol_inverse(float* Hinv, const float* Hd, int64_t m, float* w
     static const int ffma_mask = []() { const char* e = getenv("TQ_CHOL_FFMA"); return e ? atoi(e) : 0; }();
     const bool tc_potrf = !(ffma_mask & 1), tc_trtri = !(ffma_mask & 2), tc_lauum = !(ffma_mask & 4);
     int rc;
+    // operand descriptors, encoded once per inversion with the largest extents (see gemm_operands_encode)
+    GemmOperands ops_potrf, ops_trtri;
+    if (panels > 1) {
+        if (tc_potrf && (rc = gemm_operands_encode(&ops_potrf, Ph, Pl, CB, mp, Ph, Pl, CB, mp, CB))) return rc;
+        if (tc_trtri && (rc = gemm_operands_encode(&ops_trtri, Ph, Pl, CB, mp, Bh, Bl, CB, mp, CB))) return rc;
+    }
 
     static bool attr_set = false;
     const int diag_smem = (2 * CB * CB_LD + 3 * SB * (SB + 1)) * (int)sizeof(float);
@@ -357,8 +371,8 @@ extern "C" int tq_chol_inverse(float* Hinv, const float* Hd, int64_t m, float* w
             if (tc_potrf) {
                 // A_ij -= L_ik L_jk' on the tensor cores: both operands are the freshly solved panel
                 if ((rc = launch_split(L + (int64_t)(k0 + CB) * ld + k0, ld, below, CB, Ph, Pl, CB, 0, st))) return rc;
-                if ((rc = launch_gemm_tf32x3(GXM_SUB_LOWER, L + (int64_t)(k0 + CB) * ld + (k0 + CB), ld, below, below, CB,
-                                             Ph, Pl, CB, Ph, Pl, CB, nullptr, 0, st)))
+                if ((rc = launch_gemm_tf32x3_ops(GXM_SUB_LOWER, L + (int64_t)(k0 + CB) * ld + (k0 + CB), ld, below, below,
+                                                 &ops_potrf, nullptr, 0, st)))
                     return rc;
             } else {
                 chol_syrk_kernel<<<dim3(tiles, tiles), GT_THREADS, 0, st>>>(L, ld, M, k0);
@@ -381,8 +395,8 @@ extern "C" int tq_chol_inverse(float* Hinv, const float* Hd, int64_t m, float* w
                 const int64_t cend = k0 + nb;
                 if ((rc = launch_split(L + (int64_t)(k0 + CB) * ld + k0, ld, below, CB, Ph, Pl, CB, 0, st))) return rc;
                 if ((rc = launch_split(X + (int64_t)k0 * ld, ld, nb, cend, Bh, Bl, CB, 1, st))) return rc;
-                if ((rc = launch_gemm_tf32x3(GXM_SUB_RECT, X + (int64_t)(k0 + CB) * ld, ld, below, cend, nb, Ph, Pl, CB, Bh, Bl,
-                                             CB, nullptr, 0, st)))
+                if ((rc = launch_gemm_tf32x3_ops(GXM_SUB_RECT, X + (int64_t)(k0 + CB) * ld, ld, below, cend, &ops_trtri, nullptr,
+                                                 0, st)))
                     return rc;
             } else {
                 trtri_update_kernel<<<dim3(ctiles, (unsigned)ceil_div(below, GT_M)), GT_THREADS, 0, st>>>(X, ld, L, ld, M, k0);

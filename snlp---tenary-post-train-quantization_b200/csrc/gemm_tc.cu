@@ -37,6 +37,11 @@ enum GxMode {
     GX_STORE_UPPER = 3    // tiles bi <= bj, K range starts at the tile's first column; C[r, c] = acc (lauum)
 };
 
+struct GemmOperands {
+    CUtensorMap ah, al, bh, bl;
+    int64_t K;
+};
+
 struct GxProblem {
     int M, N, K;            // C is M x N, contraction length K
     int mt, nt, tiles;      // tile grid and number of scheduled tiles
@@ -356,18 +361,27 @@ int launch_split(const float* in, int64_t ld_in, int64_t rows, int64_t cols, flo
     return 0;
 }
 
-// C (op)= A B' ; A (M x K) and B (N x K) given as hi/lo pairs with leading dimensions lda / ldb (multiples of 4)
-int launch_gemm_tf32x3(int mode, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* Ah, const float* Al,
-                       int64_t lda, const float* Bh, const float* Bl, int64_t ldb, const int32_t* col_idx, int64_t col0,
-                       cudaStream_t st) {
-    if (M <= 0 || N <= 0 || K <= 0) return 0;
+// TMA descriptors of the four operand arrays.  Encoding one costs microseconds of host time, so callers that
+// launch many GEMMs over the same buffers (the sweep: one per block; the inverse: two per panel) encode once
+// with the LARGEST extents they will use: rows beyond a launch's M / N only feed accumulators the epilogue
+// never stores.
+int gemm_operands_encode(GemmOperands* ops, const float* Ah, const float* Al, int64_t lda, int64_t Mmax, const float* Bh,
+                         const float* Bl, int64_t ldb, int64_t Nmax, int64_t K) {
     TQ_CHECK_ARG((lda % 4) == 0 && (ldb % 4) == 0, "gemm_tf32x3: operand leading dimensions must be multiples of 4");
-    CUtensorMap mah, mal, mbh, mbl;
     int rc;
-    if ((rc = make_tmap_2d(&mah, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Ah, M, K, lda, GX_BM, GX_BK, "gemm_tf32x3(A hi)"))) return rc;
-    if ((rc = make_tmap_2d(&mal, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Al, M, K, lda, GX_BM, GX_BK, "gemm_tf32x3(A lo)"))) return rc;
-    if ((rc = make_tmap_2d(&mbh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Bh, N, K, ldb, GX_BN, GX_BK, "gemm_tf32x3(B hi)"))) return rc;
-    if ((rc = make_tmap_2d(&mbl, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Bl, N, K, ldb, GX_BN, GX_BK, "gemm_tf32x3(B lo)"))) return rc;
+    if ((rc = make_tmap_2d(&ops->ah, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Ah, Mmax, K, lda, GX_BM, GX_BK, "gemm_tf32x3(A hi)"))) return rc;
+    if ((rc = make_tmap_2d(&ops->al, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Al, Mmax, K, lda, GX_BM, GX_BK, "gemm_tf32x3(A lo)"))) return rc;
+    if ((rc = make_tmap_2d(&ops->bh, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Bh, Nmax, K, ldb, GX_BN, GX_BK, "gemm_tf32x3(B hi)"))) return rc;
+    if ((rc = make_tmap_2d(&ops->bl, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, Bl, Nmax, K, ldb, GX_BN, GX_BK, "gemm_tf32x3(B lo)"))) return rc;
+    ops->K = K;
+    return 0;
+}
+
+// C (op)= A B' with pre-encoded operands; M, N <= the extents the operands were encoded with
+int launch_gemm_tf32x3_ops(int mode, float* C, int64_t ldc, int64_t M, int64_t N, const GemmOperands* ops,
+                           const int32_t* col_idx, int64_t col0, cudaStream_t st) {
+    const int64_t K = ops->K;
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
     GxProblem p;
     p.M = (int)M; p.N = (int)N; p.K = (int)K;
     p.mt = (int)ceil_div(M, GX_BM);
@@ -375,7 +389,8 @@ int launch_gemm_tf32x3(int mode, float* C, int64_t ldc, int64_t M, int64_t N, in
     p.mode = mode;
     p.C = C; p.ldc = ldc; p.col_idx = col_idx; p.col0 = (int)col0;
     p.k_chunk = (mode == GX_STORE_UPPER) ? 256 : 0;
-    { const char* e = getenv("TQ_GX_DEBUG"); p.debug = e ? atoi(e) : 0; }
+    static const int dbg = []() { const char* e = getenv("TQ_GX_DEBUG"); return e ? atoi(e) : 0; }();
+    p.debug = dbg;
     if (mode == GX_SUB_LOWER) {
         p.tiles = 0;
         for (int j = 0; j < p.nt; ++j) p.tiles += (p.mt - j > 0) ? p.mt - j : 0;
@@ -393,8 +408,26 @@ int launch_gemm_tf32x3(int mode, float* C, int64_t ldc, int64_t M, int64_t N, in
     }
     const int sms = sm_count();
     const int grid = p.tiles < sms ? p.tiles : sms;
-    gemm_tf32x3_kernel<<<grid, GX_THREADS, GX_SMEM, st>>>(mah, mal, mbh, mbl, p);
+    gemm_tf32x3_kernel<<<grid, GX_THREADS, GX_SMEM, st>>>(ops->ah, ops->al, ops->bh, ops->bl, p);
     TQ_LAUNCH_CHECK("gemm_tf32x3_kernel");
+    return 0;
+}
+
+int launch_gemm_tf32x3(int mode, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* Ah, const float* Al,
+                       int64_t lda, const float* Bh, const float* Bl, int64_t ldb, const int32_t* col_idx, int64_t col0,
+                       cudaStream_t st) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    GemmOperands ops;
+    int rc;
+    if ((rc = gemm_operands_encode(&ops, Ah, Al, lda, M, Bh, Bl, ldb, N, K))) return rc;
+    return launch_gemm_tf32x3_ops(mode, C, ldc, M, N, &ops, col_idx, col0, st);
+}
+
+int launch_feedback_coef(const float* Hinv, int64_t ldh, const int32_t* blk_idx, int64_t blk0, int64_t b,
+                         const int32_t* rem_idx, int64_t rem0, int64_t rem, float* ch, float* cl, int64_t ldb, cudaStream_t st) {
+    dim3 grid((unsigned)ceil_div(rem, 32), (unsigned)ceil_div(b, 32));
+    feedback_coef_kernel<<<grid, 256, 0, st>>>(Hinv, ldh, blk_idx, (int)blk0, (int)b, rem_idx, (int)rem0, (int)rem, ch, cl, ldb);
+    TQ_LAUNCH_CHECK("feedback_coef_kernel");
     return 0;
 }
 
@@ -406,9 +439,8 @@ int launch_err_feedback_tc(float* W, int64_t ldw, int64_t n, const float* Eh, co
     if (rem <= 0) return 0;
     float* ch = coef_ws;
     float* cl = coef_ws + rem * ldb;
-    dim3 grid((unsigned)ceil_div(rem, 32), (unsigned)ceil_div(b, 32));
-    feedback_coef_kernel<<<grid, 256, 0, st>>>(Hinv, ldh, blk_idx, (int)blk0, (int)b, rem_idx, (int)rem0, (int)rem, ch, cl, ldb);
-    TQ_LAUNCH_CHECK("feedback_coef_kernel");
+    int rc;
+    if ((rc = launch_feedback_coef(Hinv, ldh, blk_idx, blk0, b, rem_idx, rem0, rem, ch, cl, ldb, st))) return rc;
     return launch_gemm_tf32x3(GX_FEEDBACK, W, ldw, n, rem, b, Eh, El, lde, ch, cl, ldb, rem_idx, rem0, st);
 }
 

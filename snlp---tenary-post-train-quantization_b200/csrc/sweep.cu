@@ -4,13 +4,21 @@
 // are gone: the permutation, the remaining-column list and the AGA vector all stay on the device.
 #include "common.cuh"
 
+#include <cuda.h>
+
 namespace tq {
 
 int launch_atq_block(const float*, int64_t, int64_t, const int32_t*, int64_t, int64_t, const float*, int, int8_t*,
                      int64_t, float*, float*, int64_t, float*, float*, int64_t, int32_t*, cudaStream_t);
-int launch_err_feedback_tc(float*, int64_t, int64_t, const float*, const float*, int64_t, const float*, int64_t,
-                           const int32_t*, int64_t, int64_t, const int32_t*, int64_t, int64_t, float*, int64_t,
-                           cudaStream_t);
+struct GemmOperands {
+    CUtensorMap ah, al, bh, bl;
+    int64_t K;
+};
+int gemm_operands_encode(GemmOperands*, const float*, const float*, int64_t, int64_t, const float*, const float*, int64_t,
+                         int64_t, int64_t);
+int launch_gemm_tf32x3_ops(int, float*, int64_t, int64_t, int64_t, const GemmOperands*, const int32_t*, int64_t, cudaStream_t);
+int launch_feedback_coef(const float*, int64_t, const int32_t*, int64_t, int64_t, const int32_t*, int64_t, int64_t, float*,
+                         float*, int64_t, cudaStream_t);
 int launch_aga_vector(const float*, int64_t, const int32_t*, int64_t, int64_t, int, float*, cudaStream_t);
 int launch_ssr_stats(const float*, int64_t, int64_t, const int32_t*, int64_t, float*, float*, cudaStream_t);
 int launch_ssr_select(const float*, int64_t, const float*, int64_t, const float*, const int32_t*, int64_t, int64_t,
@@ -110,6 +118,19 @@ extern "C" int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const
         TQ_CUDA(cudaMemcpyAsync(perm, static_perm, sizeof(int32_t) * m, cudaMemcpyDeviceToDevice, st));
     }
 
+    // TMA descriptors of the feedback GEMM's operands: E (hi, lo) [n, b] and the coefficient operand (hi, lo)
+    // [remaining, b].  Encoded once for the full-width blocks (and once more if the last block is ragged); the
+    // coefficient operand is declared with m rows -- rows past the current `rem` only reach masked outputs.
+    float* coef_hi = ws.coef;
+    float* coef_lo = ws.coef + m * ldb;
+    GemmOperands ops_full, ops_tail;
+    const int64_t tail = m % block;
+    if (tc_feedback) {
+        if (m > block && (rc = gemm_operands_encode(&ops_full, ws.E, ws.E_lo, ldb, n, coef_hi, coef_lo, ldb, m, block))) return rc;
+        if (tail != 0 && m > tail && (rc = gemm_operands_encode(&ops_tail, ws.E, ws.E_lo, ldb, n, coef_hi, coef_lo, ldb, m, tail)))
+            return rc;
+    }
+
     int cur = 0;
     int64_t done = 0, rem = m;
     for (int64_t k = 0; done < m; ++k) {
@@ -153,10 +174,12 @@ extern "C" int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const
                                    nb, ws.E, tc_feedback ? ws.E_lo : nullptr, ldb, nullptr, st)))
             return rc;
         if (rem > 0) {                                            // gptq.py:170 (and SURVEY Q3)
-            if (tc_feedback)
-                rc = launch_err_feedback_tc(W, ldw, n, ws.E, ws.E_lo, ldb, Hinv, m, blk_idx, done, b, rem_idx, done + b,
-                                            rem, ws.coef, ldb, st);
-            else
+            if (tc_feedback) {
+                if ((rc = launch_feedback_coef(Hinv, m, blk_idx, done, b, rem_idx, done + b, rem, coef_hi, coef_lo, ldb, st)))
+                    return rc;
+                rc = launch_gemm_tf32x3_ops(0 /* GX_FEEDBACK */, W, ldw, n, rem, (b == block) ? &ops_full : &ops_tail, rem_idx,
+                                            done + b, st);
+            } else
                 rc = launch_err_feedback(W, ldw, n, ws.E, ldb, Hinv, m, blk_idx, done, b, rem_idx, done + b, rem, st);
             if (rc) return rc;
         }

@@ -175,6 +175,14 @@ class GPTQ:
         """gptq.py:78-199.  New optional arguments keep the reference's behaviour by default:
         aga   'hessian' (gptq.py:147-150) | 'activations' (main.py:177-180) | 'none'
         order None -> 'ssr' if use_ssr else 'sequential'; 'actorder' = descending diag(H) (extension)."""
+        self.enqueue(use_ssr=use_ssr, aga=aga, order=order, max_iter=max_iter)
+        return self.finish()
+
+    @torch.no_grad()
+    def enqueue(self, use_ssr: bool = True, aga: str = "hessian", order: Optional[str] = None, max_iter: int = 100):
+        """Asynchronous half of quantize(): enqueue prologue (scale + damp, Cholesky inverse) and the whole
+        column sweep on the CURRENT stream and return without touching the host again.  finish() must follow.
+        A layer driver enqueues several linears on different streams before finishing any of them."""
         lib = _lib.load()
         if aga not in _AGA:
             raise ValueError(f"aga must be one of {sorted(_AGA)}")
@@ -212,14 +220,26 @@ class GPTQ:
 
         if aga == "activations":
             self.state.full()            # the AGA Gram reads H[blk, blk] on both sides of the diagonal
-        alpha, mu, T8, perm = run(Hinv)
-        self.info = int(info.item())     # the one host sync of the layer
-        if self.info != 0:
-            # gptq.py:104-106: Cholesky failed -> pseudo-inverse (library SVD, as in the reference), redo the sweep
-            Hinv = torch.linalg.pinv(Hd)
-            self.state._cache[float(self.percdamp)] = (Hd, Hinv, torch.zeros_like(info))
-            alpha, mu, T8, perm = run(Hinv)
+        self._pending = (run, Hd, info, run(Hinv), torch.cuda.current_stream(dev))
 
+    @torch.no_grad()
+    def finish(self) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Synchronous half of quantize(): read the Cholesky status (the one host sync of the layer), take the
+        reference's pseudo-inverse route if the factorisation failed (gptq.py:104-106), publish the results."""
+        if getattr(self, "_pending", None) is None:
+            raise RuntimeError("finish() without enqueue()")
+        run, Hd, info, (alpha, mu, T8, perm), stream = self._pending
+        self._pending = None
+        # everything was enqueued on `stream`, which need not be the caller's current stream: wait for it before
+        # touching any result from the host or from another stream
+        stream.synchronize()
+        self.info = int(info.item())
+        if self.info != 0:
+            with torch.cuda.stream(stream):
+                Hinv = torch.linalg.pinv(Hd)          # library SVD, as in the reference
+                self.state._cache[float(self.percdamp)] = (Hd, Hinv, torch.zeros_like(info))
+                alpha, mu, T8, perm = run(Hinv)
+            stream.synchronize()
         self.alpha = alpha.to(self.dtype)
         self.mu = mu.to(self.dtype)
         self.T_int8 = T8

@@ -27,6 +27,66 @@ class LinearView(_Weight):
     pass
 
 
+class LayerDriver:
+    """Device-resident driver for the linears of one transformer layer (the loop of main.py:289-299).
+
+    The linears are independent once their Hessians exist, and each one's prologue + sweep is a long chain
+    of small dependent kernels, so the chains of different linears are enqueued on different CUDA streams
+    and overlap on the GPU; the Hessian GEMMs, which saturate the device, stay on the caller's stream."""
+
+    def __init__(self, device, block_size: int = 128, percdamp: float = 0.01, num_streams: int = 4,
+                 share_inputs: bool = False):
+        self.device = torch.device(device)
+        self.block_size, self.percdamp, self.share_inputs = block_size, percdamp, share_inputs
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(max(1, num_streams))]
+
+    def quantize(self, linears, use_ssr: bool = True, aga: str = "hessian", max_iter: int = 100, hess_timing=None):
+        """linears: [(name, W (n, m) CUDA fp32, X (.., m) CUDA activations)].  Linears handed the SAME X object
+        share one Hessian when share_inputs is set.  Returns [GPTQ] in order, quantized."""
+        main = torch.cuda.current_stream(self.device)
+        shared = {}
+        gs = []
+        for name, W, X in linears:
+            st = shared.get(id(X)) if self.share_inputs else None
+            g = GPTQ(LinearView(W), self.block_size, self.percdamp, hessian=st)
+            if st is None:
+                if hess_timing is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                g.add_batch(X)
+                if hess_timing is not None:
+                    e1.record()
+                    hess_timing.append((e0, e1, X.numel() // X.shape[-1], W.shape[1]))
+                if self.share_inputs:
+                    shared[id(X)] = g.state
+            gs.append(g)
+        import os, time
+        dbg = os.environ.get("TQ_DRIVER_DEBUG")
+        if dbg:
+            torch.cuda.synchronize()
+            print(f"[driver] hessians done", flush=True)
+            t_enq = time.perf_counter()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        # longest chains first so the tail is short
+        order = sorted(range(len(gs)), key=lambda i: -(gs[i].columns ** 2 + gs[i].rows * gs[i].columns / 8))
+        for slot, i in enumerate(order):
+            s = self.streams[slot % len(self.streams)]
+            s.wait_event(ready)
+            with torch.cuda.stream(s):
+                gs[i].enqueue(use_ssr=use_ssr, aga=aga, max_iter=max_iter)
+        if dbg:
+            print(f"[driver] enqueue of all linears took {1e3 * (time.perf_counter() - t_enq):.1f} ms host time", flush=True)
+        for i in order:
+            t0 = time.perf_counter()
+            gs[i].finish()
+            if dbg:
+                print(f"[driver] finish {linears[i][0]}: {1e3 * (time.perf_counter() - t0):.1f} ms info={gs[i].info}", flush=True)
+        for s in self.streams:
+            main.wait_stream(s)
+        return gs
+
+
 class HostPipeline:
     def __init__(self, device, block_size: int = 128, percdamp: float = 0.01, use_ssr: bool = True,
                  aga: str = "hessian", share_inputs: bool = False):

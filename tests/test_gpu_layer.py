@@ -181,3 +181,30 @@ def test_get_quantized_weight_before_quantize_raises():
         g.get_quantized_weight()
     with pytest.raises(RuntimeError, match="before add_batch"):
         g.quantize()
+
+
+def test_layer_driver_streams_match_sequential():
+    """LayerDriver spreads the per-linear prologue+sweep chains over CUDA streams; results must equal the plain
+    one-linear-at-a-time API bit for bit, also when earlier results are still alive (regression: finish() used to
+    read the Cholesky status on the caller's stream before the side stream had produced it)."""
+    import tq100
+    from tq100.pipeline import LayerDriver
+    shapes = [("a", 384, 640), ("b", 640, 384), ("c", 300, 520)]
+    Ws = {nm: torch.from_numpy(synth.make_weight(n, m, seed=200 + i)).to(DEV) for i, (nm, n, m) in enumerate(shapes)}
+    Xs = {m: torch.from_numpy(synth.make_activations(4, 256, m, seed=300 + m)).to(DEV) for m in (640, 384, 520)}
+    ref = {}
+    for nm, n, m in shapes:
+        g = tq100.GPTQ(_layer(Ws[nm].cpu().numpy()))
+        g.add_batch(Xs[m])
+        a, u, T, p = g.quantize(use_ssr=True)
+        ref[nm] = (a.clone(), u.clone(), T.clone(), p.clone())
+    keep = []
+    for streams in (1, 2, 3):
+        drv = LayerDriver(DEV, num_streams=streams)
+        for rep in range(3):
+            gs = drv.quantize([(nm, Ws[nm], Xs[m]) for nm, n, m in shapes], use_ssr=True)
+            keep.append(gs)
+            for g, (nm, n, m) in zip(gs, shapes):
+                assert g.info == 0
+                a, u, T, p = ref[nm]
+                assert torch.equal(g.perm, p) and torch.equal(g.T, T) and torch.equal(g.alpha, a) and torch.equal(g.mu, u)
