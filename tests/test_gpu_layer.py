@@ -184,9 +184,10 @@ def test_get_quantized_weight_before_quantize_raises():
 
 
 def test_layer_driver_streams_match_sequential():
-    """LayerDriver spreads the per-linear prologue+sweep chains over CUDA streams; results must equal the plain
-    one-linear-at-a-time API bit for bit, also when earlier results are still alive (regression: finish() used to
-    read the Cholesky status on the caller's stream before the side stream had produced it)."""
+    """LayerDriver spreads the per-linear prologue+sweep chains over CUDA streams; results must match the plain
+    one-linear-at-a-time API (to parity tolerance: the Hessian's reduce-add order is not fixed run to run), also
+    when earlier results are still alive (regression: finish() used to read the Cholesky status on the caller's
+    stream before the side stream had produced it)."""
     import tq100
     from tq100.pipeline import LayerDriver
     shapes = [("a", 384, 640), ("b", 640, 384), ("c", 300, 520)]
@@ -197,7 +198,7 @@ def test_layer_driver_streams_match_sequential():
         g = tq100.GPTQ(_layer(Ws[nm].cpu().numpy()))
         g.add_batch(Xs[m])
         a, u, T, p = g.quantize(use_ssr=True)
-        ref[nm] = (a.clone(), u.clone(), T.clone(), p.clone())
+        ref[nm] = dict(alpha=a.cpu().numpy(), mu=u.cpu().numpy(), T=T.cpu().numpy(), perm=p.cpu().numpy())
     keep = []
     for streams in (1, 2, 3):
         drv = LayerDriver(DEV, num_streams=streams)
@@ -206,5 +207,5 @@ def test_layer_driver_streams_match_sequential():
             keep.append(gs)
             for g, (nm, n, m) in zip(gs, shapes):
                 assert g.info == 0
-                a, u, T, p = ref[nm]
-                assert torch.equal(g.perm, p) and torch.equal(g.T, T) and torch.equal(g.alpha, a) and torch.equal(g.mu, u)
+                got = dict(alpha=g.alpha.cpu().numpy(), mu=g.mu.cpu().numpy(), T=g.T.cpu().numpy(), perm=g.perm.cpu().numpy())
+                parity.assert_layer_parity(got, ref[nm], what=f"{nm}/streams={streams}/rep={rep}")
