@@ -336,6 +336,52 @@ def main():
                        "copied from pinned host memory on a side stream (double-buffered against compute), "
                        "alpha/mu/T(int8)/perm copied back to pinned host memory; wall clock around all 32 layers"}
         del host_acts, host_w, pipe, res
+    elif not args.no_e2e:
+        # N > 1: every rank streams ITS calibration samples and ITS row slab of the weights from pinned host memory,
+        # runs the sharded layer (all-reduce of H, dealt inverses, row-slab sweeps), and copies its slabs of
+        # alpha / mu / T (int8) and perm back to pinned host memory.
+        host_acts = {k: v.cpu().pin_memory() for k, v in acts.items()}                    # already this rank's samples
+        slabs = {name: ctx.row_range(n) for name, n, m, _ in lins}
+        host_w = {name: weights[0][name][slabs[name][0]:slabs[name][1]].cpu().pin_memory() for name, _, _, _ in lins}
+        dev_acts = {k: torch.empty_like(v) for k, v in acts.items()}
+        dev_w = {name: torch.empty_like(weights[0][name]) for name, _, _, _ in lins}
+        h2d = d2h = 0
+
+        def one_layer():
+            nonlocal h2d, d2h
+            for k in host_acts:
+                dev_acts[k].copy_(host_acts[k], non_blocking=True)
+                h2d += host_acts[k].numel() * host_acts[k].element_size()
+            for name, (lo, hi) in slabs.items():
+                dev_w[name][lo:hi].copy_(host_w[name], non_blocking=True)
+                h2d += host_w[name].numel() * 4
+            out = sharded_layer.quantize([(name, dev_w[name], dev_acts[src]) for name, n, m, src in lins], use_ssr=True)
+            res = []
+            for name, alpha, mu, T8, perm, _ in out:
+                for t in (alpha, mu, T8, perm):
+                    hbuf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                    hbuf.copy_(t, non_blocking=True)
+                    d2h += t.numel() * t.element_size()
+                    res.append(hbuf)
+            return res
+
+        one_layer()
+        barrier()
+        h2d = d2h = 0
+        t0 = time.perf_counter()
+        for _ in range(cfg["layers"]):
+            keep = one_layer()
+        barrier()
+        dt = time.perf_counter() - t0
+        e2e = {"value": dt, "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "note": "per rank: its calibration samples and its row slab of each weight copied from pinned host memory, "
+                       "ShardedLayer.quantize, its slabs of alpha/mu/T(int8) + perm copied back; bytes are per rank; "
+                       "wall clock around all layers with barriers, max over ranks"}
+        del host_acts, host_w, dev_acts, dev_w, keep
+    if e2e is not None and world > 1:
+        t = torch.tensor([e2e["value"]], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e["value"] = float(t.item())
     if rank == 0:
         line = {"metric": "LLaMA-2-7B ternary PTQ wall-time", "value": value, "unit": "s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,

@@ -88,8 +88,8 @@ int tq_chol_inverse(float* Hinv, const float* Hd, int64_t m, float* work, int* i
  * Stage 2 (one CTA): similarities, top-`block` (descending, ties -> lower position), the new
  *   remaining list (order kept).  Between the stages a row-sharded caller all-reduces
  *   `partials` and the scalar sum of rowmean^2 (pass it in wbar_sq_dev, else NULL).
- *   sims f32 [2*rem]: first rem entries = compute_column_similarity_to_mean's return value, the rest
- *   is scratch for the selection keys. */
+ *   sims f32 [2*rem + 2]: first rem entries = compute_column_similarity_to_mean's return value, the
+ *   rest is scratch (selection keys, ||wbar||^2). */
 int64_t tq_ssr_num_chunks(int64_t n);
 int tq_ssr_stats(const float* W, int64_t ldw, int64_t n, const int32_t* rem_idx, int64_t rem,
                  float* rowmean, float* partials, void* stream);
@@ -173,7 +173,8 @@ int tq_unpack2b(const uint8_t* packed, int64_t count, int8_t* T, void* stream);
  *          statistics are all-reduced (2*rem+1 floats, NCCL, on `stream`) so every rank selects the
  *          same block; sequential / static orders need no exchange. */
 #define TQ_SWEEP_ROW_SHARD 1
-#define TQ_SWEEP_FFMA_FEEDBACK 2   /* error feedback on the fp32 CUDA cores instead of the 3xTF32 tcgen05 GEMM */
+#define TQ_SWEEP_FFMA_FEEDBACK 2   /* error feedback on the fp32 CUDA cores instead of the split-TF32 tcgen05 GEMM */
+#define TQ_SWEEP_UNFUSED_STATS 4   /* SSR statistics by two passes over W per block instead of from the feedback epilogue */
 int64_t tq_sweep_workspace_bytes(int64_t n, int64_t m, int64_t block);
 int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const float* Hd, const float* Hraw,
                    const float* Hinv, int64_t block, int order, int aga, int max_iter,

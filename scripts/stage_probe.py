@@ -94,7 +94,7 @@ def main():
         partials = torch.empty((chunks, 2, m), device=DEV)
         blk = torch.empty(128, device=DEV, dtype=torch.int32)
         newrem = torch.empty(m, device=DEV, dtype=torch.int32)
-        sims = torch.empty(2 * m, device=DEV)
+        sims = torch.empty(2 * m + 2, device=DEV)
         def stats():
             _lib.check(lib.tq_ssr_stats(_lib.ptr(Wd), m, n, _lib.ptr(remv), m, _lib.ptr(rowmean), _lib.ptr(partials), _lib.stream()), "stats")
         def select():

@@ -16,6 +16,7 @@ AGA_NONE, AGA_HESSIAN, AGA_ACTIVATIONS = 0, 1, 2
 ORDER_SEQUENTIAL, ORDER_SSR, ORDER_STATIC = 0, 1, 2
 SWEEP_ROW_SHARD = 1
 SWEEP_FFMA_FEEDBACK = 2
+SWEEP_UNFUSED_STATS = 4
 OP_INIT, OP_GRID, OP_ROUND, OP_ITF, OP_AGA = 0, 1, 2, 3, 4
 
 _i64 = ctypes.c_int64

@@ -195,7 +195,9 @@ __global__ void __launch_bounds__(256)
 atq_block_kernel(const float* __restrict__ W, int64_t ldw, int n, const int32_t* __restrict__ blk_idx, int col0,
                  int b, const float* __restrict__ s1d, int max_iter, int8_t* __restrict__ T, int64_t ldt,
                  float* __restrict__ alpha_out, float* __restrict__ mu_out, int64_t ld_am,
-                 float* __restrict__ E, float* __restrict__ E_lo, int64_t lde, int32_t* __restrict__ iters_out) {
+                 float* __restrict__ E, float* __restrict__ E_lo, int64_t lde, int32_t* __restrict__ iters_out,
+                 const double* __restrict__ rowsum_cur, const double* __restrict__ csum, int rem_next,
+                 float* __restrict__ wbar_next) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= n) return;
@@ -212,6 +214,25 @@ atq_block_kernel(const float* __restrict__ W, int64_t ldw, int n, const int32_t*
         if (iters_out) iters_out[row] = it;
     }
     r.store_codes(T + (int64_t)row * ldt, b, ((ldt & 3) == 0) && ((reinterpret_cast<uintptr_t>(T) & 3) == 0));
+    if (wbar_next != nullptr) {
+        // SSR bookkeeping for the NEXT selection: the row sum over the next remaining set, predicted exactly from
+        // this block's removal and feedback:  sum_new = sum_cur - sum(W_b) - E . (C 1)   (gptq.py:186 summed over j)
+        double bs = 0.0, ec = 0.0;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+            if (r.valid[e]) {
+                const float ev = __fsub_rn(r.w[e], __fadd_rn(__fmul_rn(alpha, (float)r.t[e]), mu));
+                bs += (double)r.w[e];
+                ec += (double)ev * csum[r.p0 + e];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            bs += __shfl_xor_sync(0xffffffffu, bs, o);
+            ec += __shfl_xor_sync(0xffffffffu, ec, o);
+        }
+        if (lane == 0) wbar_next[row] = (float)((rowsum_cur[row] - bs - ec) / (double)rem_next);
+    }
     if (E != nullptr)
         r.store_error(E + (int64_t)row * lde, E_lo ? E_lo + (int64_t)row * lde : nullptr, b, alpha, mu,
                       ((lde & 3) == 0) && ((reinterpret_cast<uintptr_t>(E) & 15) == 0) &&
@@ -302,14 +323,32 @@ aga_vector_kernel(const float* __restrict__ Hsrc, int64_t ldh, const int32_t* __
     }
 }
 
+// csum[i] = sum over all coefficient-kernel CTAs of their partial column sums, in a fixed order, in double
+__global__ void __launch_bounds__(128)
+csum_fold_kernel(const float* __restrict__ csum_part, int parts, int b, double* __restrict__ csum) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= b) return;
+    double s = 0.0;
+    for (int t = 0; t < parts; ++t) s += (double)csum_part[(int64_t)t * b + i];
+    csum[i] = s;
+}
+
+int launch_csum_fold(const float* csum_part, int64_t parts, int64_t b, double* csum, cudaStream_t st) {
+    csum_fold_kernel<<<(unsigned)ceil_div(b, 128), 128, 0, st>>>(csum_part, (int)parts, (int)b, csum);
+    TQ_LAUNCH_CHECK("csum_fold_kernel");
+    return 0;
+}
+
 int launch_atq_block(const float* W, int64_t ldw, int64_t n, const int32_t* blk_idx, int64_t col0, int64_t b,
                      const float* s1d, int max_iter, int8_t* T, int64_t ldt, float* alpha, float* mu,
-                     int64_t ld_am, float* E, float* E_lo, int64_t lde, int32_t* iters, cudaStream_t st) {
+                     int64_t ld_am, float* E, float* E_lo, int64_t lde, int32_t* iters, const double* rowsum_cur,
+                     const double* csum, int64_t rem_next, float* wbar_next, cudaStream_t st) {
     const int warps = 8;
     dim3 grid((unsigned)ceil_div(n, warps)), block(warps * 32);
 #define TQ_ATQ_CASE(EPL)                                                                                      \
     atq_block_kernel<EPL><<<grid, block, 0, st>>>(W, ldw, (int)n, blk_idx, (int)col0, (int)b, s1d, max_iter, \
-                                                  T, ldt, alpha, mu, ld_am, E, E_lo, lde, iters)
+                                                  T, ldt, alpha, mu, ld_am, E, E_lo, lde, iters, rowsum_cur, csum,     \
+                                                  (int)rem_next, wbar_next)
     if (b <= 32) TQ_ATQ_CASE(1);
     else if (b <= 64) TQ_ATQ_CASE(2);
     else if (b <= 128) TQ_ATQ_CASE(4);
@@ -338,7 +377,7 @@ extern "C" int tq_atq_block(const float* W, int64_t ldw, int64_t n, const int32_
                  (long long)n, (long long)b);
     TQ_CHECK_ARG(ldt >= b && ld_am >= 1 && (E == nullptr || lde >= b) && max_iter >= 0, "tq_atq_block: bad strides");
     return launch_atq_block(W, ldw, n, blk_idx, col0, b, s1d, max_iter, T, ldt, alpha, mu, ld_am, E, nullptr, lde, iters,
-                            (cudaStream_t)stream);
+                            nullptr, nullptr, 0, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int tq_atq_stage(int op, const float* W, int64_t ldw, int64_t n, int64_t b, const int8_t* T_in,

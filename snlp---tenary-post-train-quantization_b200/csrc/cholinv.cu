@@ -16,9 +16,12 @@
 // A non-positive pivot is reported through *info (1-based index, LAPACK convention); the caller takes
 // the reference's pinv route (gptq.py:104-106).
 #include "gemm_simt.cuh"
+#include "tc_common.cuh"
 
 #include <cuda.h>
 #include <stdlib.h>
+#include <unordered_map>
+#include <vector>
 
 namespace tq {
 
@@ -34,7 +37,10 @@ constexpr int DIAG_THREADS = 512;
 constexpr int SB = 32;                 // sub-block width
 constexpr int NSB = CB / SB;           // 4
 
-__device__ __forceinline__ void diag_factor_32(float* S, int o, int nb, int k0, int* info, int lane) {
+// One warp factors a 32x32 diagonal sub-block; lane i holds row i in registers.  Each column step publishes the
+// freshly scaled column through a 32-float shared buffer that every lane reads back as eight 128-bit broadcast
+// loads (independent, so they pipeline -- a shuffle per multiplier would stall the in-order issue 31 times).
+__device__ __forceinline__ void diag_factor_32(float* S, float* colbuf, int o, int nb, int k0, int* info, int lane) {
     float a[SB];
 #pragma unroll
     for (int c = 0; c < SB; ++c) a[c] = S[(o + lane) * CB_LD + o + c];
@@ -45,41 +51,75 @@ __device__ __forceinline__ void diag_factor_32(float* S, int o, int nb, int k0, 
             if (lane == 0 && o + j < nb) atomicCAS(info, 0, k0 + o + j + 1);
             pj = 1.f;                                        // keep going so nothing downstream divides by zero
         }
-        const float dj = sqrtf(pj);
-        const float l = (lane == j) ? dj : __fdiv_rn(a[j], dj);
+        const float rinv = __frsqrt_rn(pj);
+        const float l = (lane == j) ? __fmul_rn(pj, rinv) : __fmul_rn(a[j], rinv);
         a[j] = l;
+        colbuf[lane] = l;
+        __syncwarp();
+        float lc[SB];
 #pragma unroll
-        for (int c = j + 1; c < SB; ++c) {
-            const float lc = __shfl_sync(0xffffffffu, l, c);
-            if (lane >= c) a[c] = fmaf(-l, lc, a[c]);
+        for (int v = 0; v < SB / 4; ++v) {
+            const float4 t = *reinterpret_cast<const float4*>(colbuf + 4 * v);
+            lc[4 * v] = t.x; lc[4 * v + 1] = t.y; lc[4 * v + 2] = t.z; lc[4 * v + 3] = t.w;
         }
+#pragma unroll
+        for (int c = j + 1; c < SB; ++c)
+            if (lane >= c) a[c] = fmaf(-l, lc[c], a[c]);
+        __syncwarp();
     }
 #pragma unroll
     for (int c = 0; c < SB; ++c) S[(o + lane) * CB_LD + o + c] = (c <= lane) ? a[c] : 0.f;
 }
 
 __global__ void __launch_bounds__(DIAG_THREADS)
-chol_diag_kernel(float* __restrict__ A, int64_t ld, int m, int k0, float* __restrict__ Dk, int* __restrict__ info) {
+chol_diag_kernel(float* __restrict__ A, int64_t ld, int m, int k0, float* __restrict__ Dk, int* __restrict__ info,
+                 long long* __restrict__ prof) {
     extern __shared__ float sh[];
+    int pi = 0;
+#define TQ_PROF() do { if (prof && threadIdx.x == 0) prof[pi++] = clock64(); } while (0)
+    TQ_PROF();
     float* S = sh;                       // [CB][CB_LD]  A_kk -> L_kk
     float* V = sh + CB * CB_LD;          // [CB][CB_LD]  L_kk^-1
     float* Tm = sh + 2 * CB * CB_LD;     // [3][SB][SB+1] scratch for the off-diagonal inverse blocks
+    __shared__ __align__(16) float colbuf[SB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nb = min(CB, m - k0);
-    for (int e = tid; e < CB * CB; e += DIAG_THREADS) {
-        const int i = e >> 7, j = e & (CB - 1);
-        float v = (i == j) ? 1.f : 0.f;                          // identity padding for a ragged last panel
-        if (i < nb && j < nb) v = (j <= i) ? A[(int64_t)(k0 + i) * ld + k0 + j] : 0.f;
-        S[i * CB_LD + j] = v;
-        V[i * CB_LD + j] = 0.f;
+    // tid -> (row = tid / 4 + 128 * ..., 32 consecutive columns): each thread fetches its 32 values with eight
+    // independent 128-bit loads when the block is interior and aligned, else element-wise
+    {
+        const int i = tid >> 2, j0 = (tid & 3) * 32;
+        const bool fast = (nb == CB) && ((ld & 3) == 0) && ((k0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+        float vals[32];
+        if (fast) {
+            const float4* src = reinterpret_cast<const float4*>(A + (int64_t)(k0 + i) * ld + k0 + j0);
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                const float4 t = src[v];
+                vals[4 * v] = t.x; vals[4 * v + 1] = t.y; vals[4 * v + 2] = t.z; vals[4 * v + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const int j = j0 + c;
+                vals[c] = (i < nb && j < nb) ? A[(int64_t)(k0 + i) * ld + k0 + j] : ((i == j) ? 1.f : 0.f);   // identity padding
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const int j = j0 + c;
+            S[i * CB_LD + j] = (j <= i) ? vals[c] : 0.f;
+            V[i * CB_LD + j] = 0.f;
+        }
     }
     __syncthreads();
+    TQ_PROF();
 
     // ---- L = chol(S), right-looking over 32-column steps
     for (int d = 0; d < NSB; ++d) {
         const int o = d * SB;
-        if (warp == 0) diag_factor_32(S, o, nb, k0, info, lane);
+        if (warp == 0) diag_factor_32(S, colbuf, o, nb, k0, info, lane);
         __syncthreads();
+        TQ_PROF();
         const int below = CB - o - SB;                           // rows under the diagonal sub-block
         if (tid < below) {                                       // x L_dd' = a : one row per thread
             float* row = S + (o + SB + tid) * CB_LD + o;
@@ -95,6 +135,7 @@ chol_diag_kernel(float* __restrict__ A, int64_t ld, int m, int k0, float* __rest
             for (int j = 0; j < SB; ++j) row[j] = x[j];
         }
         __syncthreads();
+        TQ_PROF();
         if (below > 0) {                                         // trailing -= P P', 4 threads per row
             const int r = o + SB + (tid >> 2);
             if (r < CB) {
@@ -110,6 +151,7 @@ chol_diag_kernel(float* __restrict__ A, int64_t ld, int m, int k0, float* __rest
             }
         }
         __syncthreads();
+        TQ_PROF();
     }
 
     // ---- V = L^-1: diagonal sub-blocks, one warp each, lane = column of the inverse
@@ -127,6 +169,7 @@ chol_diag_kernel(float* __restrict__ A, int64_t ld, int m, int k0, float* __rest
         for (int i = 0; i < SB; ++i) V[(o + i) * CB_LD + o + lane] = x[i];
     }
     __syncthreads();
+    TQ_PROF();
     // off-diagonal sub-blocks, level by level:  V_ij = -V_ii * sum_{k=j}^{i-1} L_ik V_kj
     for (int lev = 1; lev < NSB; ++lev) {
         const int nblk = NSB - lev;                              // blocks (i, j) = (j + lev, j)
@@ -159,12 +202,16 @@ chol_diag_kernel(float* __restrict__ A, int64_t ld, int m, int k0, float* __rest
             for (int q = 0; q < 8; ++q) V[(bi * SB + er) * CB_LD + bj * SB + ec0 + q] = -acc[q];
         }
         __syncthreads();
+        TQ_PROF();
     }
     for (int e = tid; e < CB * CB; e += DIAG_THREADS) {
         const int i = e >> 7, j = e & (CB - 1);
         Dk[e] = V[i * CB_LD + j];
         if (i < nb && j < nb && j <= i) A[(int64_t)(k0 + i) * ld + k0 + j] = S[i * CB_LD + j];
     }
+    __syncthreads();
+    TQ_PROF();
+#undef TQ_PROF
 }
 
 // L_ik = A_ik D_k'   (rows below the panel), in place
@@ -295,25 +342,48 @@ lauum_kernel(float* __restrict__ Hinv, int64_t ldh, const float* __restrict__ X,
     }
 }
 
-int launch_split(const float*, int64_t, int64_t, int64_t, float*, float*, int64_t, int, cudaStream_t);     // gemm_tc.cu
-int launch_gemm_tf32x3(int, float*, int64_t, int64_t, int64_t, int64_t, const float*, const float*, int64_t, const float*,
-                       const float*, int64_t, const int32_t*, int64_t, cudaStream_t);
-struct GemmOperands {
-    CUtensorMap ah, al, bh, bl;
-    int64_t K;
-};
-int gemm_operands_encode(GemmOperands*, const float*, const float*, int64_t, int64_t, const float*, const float*, int64_t,
-                         int64_t, int64_t);
-int launch_gemm_tf32x3_ops(int, float*, int64_t, int64_t, int64_t, const GemmOperands*, const int32_t*, int64_t, cudaStream_t);
-enum { GXM_SUB_LOWER = 1, GXM_SUB_RECT = 2, GXM_STORE_UPPER = 3 };   // GxMode of gemm_tc.cu
+long long* g_diag_prof = nullptr;
 
+// rows of the stacked L-panel splits: panel k contributes the rows below it
+static inline int64_t chol_stack_rows(int64_t m) {
+    const int64_t panels = ceil_div(m, CB);
+    int64_t rows = 0;
+    for (int64_t k = 0; k + 1 < panels; ++k) rows += m - (k + 1) * CB;
+    return rows;
+}
+
+// operand region: phases 1/2 keep the stacked (hi, lo) splits of every L panel plus the transposed strip of phase 2;
+// phase 3 reuses the region for Y = (L^-1)' (hi, lo)
 static inline int64_t chol_split_floats(int64_t m) {
     const int64_t mp = ceil_div(m, CB) * CB;
-    const int64_t a = 2 * m * m, b = 4 * mp * CB;
+    const int64_t a = 2 * m * m, b = 2 * chol_stack_rows(m) * CB + 2 * mp * CB + 2 * CB * CB;
     return a > b ? a : b;
 }
 
+// a helper stream per caller stream: phase 2 (L^-1) chases phase 1 (potrf) panel by panel
+static cudaStream_t aux_stream_for(cudaStream_t st) {
+    static std::unordered_map<cudaStream_t, cudaStream_t> pool;
+    auto it = pool.find(st);
+    if (it != pool.end()) return it->second;
+    cudaStream_t aux = nullptr;
+    if (cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    pool[st] = aux;
+    return aux;
+}
+static cudaEvent_t chol_event(size_t i) {
+    static std::vector<cudaEvent_t> pool;
+    while (pool.size() <= i) {
+        cudaEvent_t e = nullptr;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        pool.push_back(e);
+    }
+    return pool[i];
+}
+
 }  // namespace tq
+
+// development aid: device buffer (>= 32 long long) that receives clock64 stamps of the first panel's phases
+extern "C" void tq_debug_set_diag_prof(long long* dev_buf) { tq::g_diag_prof = dev_buf; }
 
 extern "C" int64_t tq_chol_workspace_floats(int64_t m) {
     const int64_t panels = tq::ceil_div(m, tq::CB);
@@ -331,19 +401,24 @@ extern "C" int tq_chol_inverse(float* Hinv, const float* Hd, int64_t m, float* w
     float* X = work;                       // L^-1
     float* D = work + m * m;               // per-panel inverses of the diagonal blocks
     const int panels = (int)ceil_div(m, CB);
-    float* S = D + (int64_t)panels * CB * CB;          // (hi, lo) operand splits for the tensor-core updates
+    float* S = D + (int64_t)panels * CB * CB;          // (hi, lo) operand region, see chol_split_floats
     const int64_t mp = (int64_t)panels * CB;
-    float *Ph = S, *Pl = S + mp * CB, *Bh = S + 2 * mp * CB, *Bl = S + 3 * mp * CB;   // panel / strip operands, ld = CB
+    const int64_t srows = chol_stack_rows(m);
+    float *Sh = S, *Sl = S + srows * CB;                                   // stacked L-panel splits, ld = CB
+    float *Bh = S + 2 * srows * CB, *Bl = Bh + mp * CB;                    // transposed strip X_k,: of phase 2
     // TQ_CHOL_FFMA bit mask selects the fp32 CUDA-core kernel per phase: 1 = potrf update, 2 = trtri update, 4 = lauum
     static const int ffma_mask = []() { const char* e = getenv("TQ_CHOL_FFMA"); return e ? atoi(e) : 0; }();
     const bool tc_potrf = !(ffma_mask & 1), tc_trtri = !(ffma_mask & 2), tc_lauum = !(ffma_mask & 4);
+    static const bool one_stream = []() { const char* e = getenv("TQ_CHOL_ONE_STREAM"); return e && atoi(e) != 0; }();
     int rc;
-    // operand descriptors, encoded once per inversion with the largest extents (see gemm_operands_encode)
+    // operand descriptors, encoded once per inversion over the whole stacked / strip arrays
     GemmOperands ops_potrf, ops_trtri;
     if (panels > 1) {
-        if (tc_potrf && (rc = gemm_operands_encode(&ops_potrf, Ph, Pl, CB, mp, Ph, Pl, CB, mp, CB))) return rc;
-        if (tc_trtri && (rc = gemm_operands_encode(&ops_trtri, Ph, Pl, CB, mp, Bh, Bl, CB, mp, CB))) return rc;
+        if (tc_potrf && (rc = gemm_operands_encode(&ops_potrf, Sh, Sl, CB, srows, Sh, Sl, CB, srows, CB))) return rc;
+        if (tc_trtri && (rc = gemm_operands_encode(&ops_trtri, Sh, Sl, CB, srows, Bh, Bl, CB, mp, CB))) return rc;
     }
+    cudaStream_t aux = one_stream ? nullptr : aux_stream_for(st);
+    cudaStream_t s2 = aux ? aux : st;                 // stream of phase 2
 
     static bool attr_set = false;
     const int diag_smem = (2 * CB * CB_LD + 3 * SB * (SB + 1)) * (int)sizeof(float);
@@ -357,60 +432,72 @@ extern "C" int tq_chol_inverse(float* Hinv, const float* Hd, int64_t m, float* w
     set_identity_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, st>>>(X, ld, M);
     TQ_LAUNCH_CHECK("set_identity_kernel");
 
-    // phase 1: potrf
+    // Phase 1 (potrf, on `st`) and phase 2 (X = L^-1, on the helper stream) run panel-interleaved: step k of phase 2
+    // needs only D_k and the solved panel k of L, both final once phase 1 has passed its trsm of panel k.
+    int64_t off = 0;                                  // first row of panel k inside the stacked splits
     for (int k = 0; k < panels; ++k) {
         const int k0 = k * CB;
+        const int nb = (M - k0 < CB) ? (M - k0) : CB;
         float* Dk = D + (int64_t)k * CB * CB;
-        chol_diag_kernel<<<1, DIAG_THREADS, diag_smem, st>>>(L, ld, M, k0, Dk, info_dev);
-        TQ_LAUNCH_CHECK("chol_diag_kernel");
         const int below = M - k0 - CB;
+        // ---- phase 1, panel k
+        chol_diag_kernel<<<1, DIAG_THREADS, diag_smem, st>>>(L, ld, M, k0, Dk, info_dev, k == 0 ? g_diag_prof : nullptr);
+        TQ_LAUNCH_CHECK("chol_diag_kernel");
         if (below > 0) {
             const int tiles = (int)ceil_div(below, GT_M);
             chol_trsm_kernel<<<tiles, GT_THREADS, 0, st>>>(L, ld, M, k0, Dk);
             TQ_LAUNCH_CHECK("chol_trsm_kernel");
+            if (tc_potrf || tc_trtri)
+                if ((rc = launch_split(L + (int64_t)(k0 + CB) * ld + k0, ld, below, CB, Sh + off * CB, Sl + off * CB, CB, 0, st)))
+                    return rc;
+        }
+        if (aux) {
+            TQ_CUDA(cudaEventRecord(chol_event(k), st));
+            TQ_CUDA(cudaStreamWaitEvent(aux, chol_event(k), 0));
+        }
+        if (below > 0) {
             if (tc_potrf) {
                 // A_ij -= L_ik L_jk' on the tensor cores: both operands are the freshly solved panel
-                if ((rc = launch_split(L + (int64_t)(k0 + CB) * ld + k0, ld, below, CB, Ph, Pl, CB, 0, st))) return rc;
-                if ((rc = launch_gemm_tf32x3_ops(GXM_SUB_LOWER, L + (int64_t)(k0 + CB) * ld + (k0 + CB), ld, below, below,
-                                                 &ops_potrf, nullptr, 0, st)))
+                if ((rc = launch_gemm_tf32x3_rows(GX_SUB_LOWER, L + (int64_t)(k0 + CB) * ld + (k0 + CB), ld, below, below,
+                                                  &ops_potrf, off, off, nullptr, 0, st)))
                     return rc;
             } else {
+                const int tiles = (int)ceil_div(below, GT_M);
                 chol_syrk_kernel<<<dim3(tiles, tiles), GT_THREADS, 0, st>>>(L, ld, M, k0);
                 TQ_LAUNCH_CHECK("chol_syrk_kernel");
             }
         }
-    }
-    // phase 2: X = L^-1
-    for (int k = 0; k < panels; ++k) {
-        const int k0 = k * CB;
-        const int nb = (M - k0 < CB) ? (M - k0) : CB;
-        const float* Dk = D + (int64_t)k * CB * CB;
+        // ---- phase 2, panel k
         const int ctiles = (int)ceil_div(k0 + nb, GT_N);
-        trtri_row_kernel<<<ctiles, GT_THREADS, 0, st>>>(X, ld, M, k0, Dk);
+        trtri_row_kernel<<<ctiles, GT_THREADS, 0, s2>>>(X, ld, M, k0, Dk);
         TQ_LAUNCH_CHECK("trtri_row_kernel");
-        const int below = M - k0 - CB;
         if (below > 0) {
             if (tc_trtri) {
-                // R_i,: -= L_ik X_k,: : A = L panel rows, B = the just-finished strip X_k,: transposed to K-major
+                // R_i,: -= L_ik X_k,: : A = stacked split of the L panel, B = the just-finished strip X_k,: transposed
                 const int64_t cend = k0 + nb;
-                if ((rc = launch_split(L + (int64_t)(k0 + CB) * ld + k0, ld, below, CB, Ph, Pl, CB, 0, st))) return rc;
-                if ((rc = launch_split(X + (int64_t)k0 * ld, ld, nb, cend, Bh, Bl, CB, 1, st))) return rc;
-                if ((rc = launch_gemm_tf32x3_ops(GXM_SUB_RECT, X + (int64_t)(k0 + CB) * ld, ld, below, cend, &ops_trtri, nullptr,
-                                                 0, st)))
+                if ((rc = launch_split(X + (int64_t)k0 * ld, ld, nb, cend, Bh, Bl, CB, 1, s2))) return rc;
+                if ((rc = launch_gemm_tf32x3_rows(GX_SUB_RECT, X + (int64_t)(k0 + CB) * ld, ld, below, cend, &ops_trtri, off, 0,
+                                                  nullptr, 0, s2)))
                     return rc;
             } else {
-                trtri_update_kernel<<<dim3(ctiles, (unsigned)ceil_div(below, GT_M)), GT_THREADS, 0, st>>>(X, ld, L, ld, M, k0);
+                trtri_update_kernel<<<dim3(ctiles, (unsigned)ceil_div(below, GT_M)), GT_THREADS, 0, s2>>>(X, ld, L, ld, M, k0);
                 TQ_LAUNCH_CHECK("trtri_update_kernel");
             }
+            off += below;
         }
     }
+    if (aux) {
+        TQ_CUDA(cudaEventRecord(chol_event(panels), aux));
+        TQ_CUDA(cudaStreamWaitEvent(st, chol_event(panels), 0));
+    }
+
     // phase 3: Hinv = X'X (upper), then mirror
     if (tc_lauum && (m % 4) == 0) {
         // Y = X' (upper triangular), Hinv = Y Y': rows of Y are K-major operands; the K range of tile (i, j <= ... )
         // starts at the tile's first column because Y[i][q] = 0 for q < i
         float *Yh = S, *Yl = S + m * m;
         if ((rc = launch_split(X, ld, m, m, Yh, Yl, m, 1, st))) return rc;
-        if ((rc = launch_gemm_tf32x3(GXM_STORE_UPPER, Hinv, ld, m, m, m, Yh, Yl, m, Yh, Yl, m, nullptr, 0, st))) return rc;
+        if ((rc = launch_gemm_tf32x3(GX_STORE_UPPER, Hinv, ld, m, m, m, Yh, Yl, m, Yh, Yl, m, nullptr, 0, st))) return rc;
     } else {
         const int nt = (int)ceil_div(m, GT_M);
         lauum_kernel<<<dim3(nt, nt), GT_THREADS, 0, st>>>(Hinv, ld, X, ld, M);

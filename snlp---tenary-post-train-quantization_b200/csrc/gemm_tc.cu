@@ -27,20 +27,9 @@ constexpr int GX_STAGE_BYTES = 4 * GX_SLAB;           // 65536
 constexpr int GX_THREADS = 384;                 // 4 control warps + 8 epilogue warps
 constexpr int GX_EPI_WARPS = 8;
 constexpr int GX_CT_LD = GX_BN + 1;                // pitch of the C tile in shared memory (bank-conflict-free both ways)
-constexpr int GX_SMEM = GX_STAGES * GX_STAGE_BYTES + 256 + GX_BM * GX_CT_LD * 4 + 1024;   // stages, barriers, C tile, slack   // stages, barriers, epilogue staging, alignment slack
+constexpr int GX_COLPART = 2 * GX_EPI_WARPS * 64 * 2 * 4;   // double-buffered per-warp column partials (dot, sq)
+constexpr int GX_SMEM = GX_STAGES * GX_STAGE_BYTES + 256 + GX_BM * GX_CT_LD * 4 + GX_COLPART + 1024;   // stages, barriers, C tile, slack   // stages, barriers, epilogue staging, alignment slack
 constexpr int GX_TMEM_COLS = 256;
-
-enum GxMode {
-    GX_FEEDBACK = 0,      // all tiles; C[r, colmap(j)] -= acc
-    GX_SUB_LOWER = 1,     // tiles bi >= bj; C[r, c] -= acc for c <= r  (potrf trailing update)
-    GX_SUB_RECT = 2,      // all tiles; C[r, c] -= acc                  (trtri update)
-    GX_STORE_UPPER = 3    // tiles bi <= bj, K range starts at the tile's first column; C[r, c] = acc (lauum)
-};
-
-struct GemmOperands {
-    CUtensorMap ah, al, bh, bl;
-    int64_t K;
-};
 
 struct GxProblem {
     int M, N, K;            // C is M x N, contraction length K
@@ -50,6 +39,13 @@ struct GxProblem {
     int64_t ldc;
     const int32_t* col_idx; // FEEDBACK: absolute column of remaining position j (NULL: col0 + j)
     int col0;
+    int a_row0, b_row0;     // first row of A / B inside the (larger) arrays the descriptors were encoded over
+    // FEEDBACK only, optional (SSR): statistics of the UPDATED C for the next block selection (reorder.py:36-61),
+    // emitted from the epilogue so W is not read again: per 128-row tile partial sums over rows of
+    // C[r,j] * wbar[r] and C[r,j]^2 for every remaining position j, and exact row sums of the updated values
+    const float* wbar;      // [M] predicted row means of the updated remaining columns
+    float* stat_partials;   // [mt][2][N]
+    double* rowsum_next;    // [M], zeroed by the caller, accumulated with atomics
     int k_chunk;            // > 0: TMEM accumulates at most k_chunk of K at a time; chunks are summed in the
                             // smem C tile with round-to-nearest fp32 adds (the tensor core's accumulate truncates)
     int debug;              // development switch (env TQ_GX_DEBUG): 1 = drain accumulators only, 2 = no prefetch loads
@@ -132,10 +128,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
                 mbar_wait(empty_bar(stage), phase ^ 1);
                 const uint32_t s0 = s_base + stage * GX_STAGE_BYTES;
                 mbar_expect_tx(full_bar(stage), GX_STAGE_BYTES);
-                tma_load_2d(s0 + 0 * GX_SLAB, &map_ah, full_bar(stage), k, bi * GX_BM);
-                tma_load_2d(s0 + 1 * GX_SLAB, &map_al, full_bar(stage), k, bi * GX_BM);
-                tma_load_2d(s0 + 2 * GX_SLAB, &map_bh, full_bar(stage), k, bj * GX_BN);
-                tma_load_2d(s0 + 3 * GX_SLAB, &map_bl, full_bar(stage), k, bj * GX_BN);
+                tma_load_2d(s0 + 0 * GX_SLAB, &map_ah, full_bar(stage), k, p.a_row0 + bi * GX_BM);
+                tma_load_2d(s0 + 1 * GX_SLAB, &map_al, full_bar(stage), k, p.a_row0 + bi * GX_BM);
+                tma_load_2d(s0 + 2 * GX_SLAB, &map_bh, full_bar(stage), k, p.b_row0 + bj * GX_BN);
+                tma_load_2d(s0 + 3 * GX_SLAB, &map_bl, full_bar(stage), k, p.b_row0 + bj * GX_BN);
                 if (++stage == GX_STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -192,8 +188,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
         float* cw = ctile + (q * 32) * GX_CT_LD + half * 64;    // this warp's 32 x 64 block
         const bool rmw = (p.mode != GX_STORE_UPPER) && p.debug != 2;
         const bool lower = (p.mode == GX_SUB_LOWER);
-        int n_item = 0;
-        for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+        const bool stats = (p.stat_partials != nullptr);
+        float* colpart = ctile + GX_BM * GX_CT_LD;               // [2][8 warps][64 cols][2]
+        int n_item = 0, n_tile = 0;
+        for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++n_tile) {
             int bi, bj;
             gx_decode(p, t, bi, bj);
             const int r0 = bi * GX_BM + q * 32;                  // first row of this warp's block
@@ -252,15 +250,59 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
                 }
                 first_chunk = false;
             }
+            if (stats) {
+                // exact row sum of the updated values of this thread's row (its 64 columns of this tile)
+                float rs = 0.f;
+                const int jbase = bj * GX_BN + half * 64;
+#pragma unroll 8
+                for (int c = 0; c < 64; ++c)
+                    if (jbase + c < p.N) rs += myrow[c];
+                if (r0 + lane < p.M) atomicAdd(p.rowsum_next + r0 + lane, (double)rs);
+            }
             __syncwarp();
             if (p.debug != 1) {
+                const float wb = (stats && r0 + lane < p.M) ? p.wbar[r0 + lane] : 0.f;
 #pragma unroll
                 for (int cg = 0; cg < NCG; ++cg) {
-                    if (col[cg] >= 0) {
-                        float* dstp = p.C + (int64_t)r0 * p.ldc + col[cg];
+                    float dot = 0.f, sq = 0.f;
+                    const bool okc = col[cg] >= 0;
+                    float* dstp = p.C + (int64_t)r0 * p.ldc + (okc ? col[cg] : 0);
 #pragma unroll 8
-                        for (int rr = 0; rr < rows; ++rr)
-                            if (!lower || col[cg] <= r0 + rr) dstp[(int64_t)rr * p.ldc] = cw[rr * GX_CT_LD + cg * 32 + lane];
+                    for (int rr = 0; rr < rows; ++rr) {
+                        const float wbr = stats ? __shfl_sync(0xffffffffu, wb, rr) : 0.f;    // warp-uniform control flow
+                        if (okc) {
+                            const float v = cw[rr * GX_CT_LD + cg * 32 + lane];
+                            if (!lower || col[cg] <= r0 + rr) dstp[(int64_t)rr * p.ldc] = v;
+                            dot = fmaf(v, wbr, dot);
+                            sq = fmaf(v, v, sq);
+                        }
+                    }
+                    if (stats) {
+                        float* cp = colpart + (((n_tile & 1) * GX_EPI_WARPS + (warp - 4)) * 64 + cg * 32 + lane) * 2;
+                        cp[0] = dot;
+                        cp[1] = sq;
+                    }
+                }
+            }
+            if (stats) {
+                // the four row-quarter warps of each column half are summed in a fixed order by the q == 0 warp
+                named_bar_sync(2, GX_EPI_WARPS * 32);
+                if (q == 0) {
+#pragma unroll
+                    for (int cg = 0; cg < NCG; ++cg) {
+                        const int j = bj * GX_BN + half * 64 + cg * 32 + lane;
+                        if (j < p.N) {
+                            float dot = 0.f, sq = 0.f;
+#pragma unroll
+                            for (int qq = 0; qq < 4; ++qq) {
+                                const float* cp = colpart + (((n_tile & 1) * GX_EPI_WARPS + (half * 4 + qq)) * 64 + cg * 32 + lane) * 2;
+                                dot += cp[0];
+                                sq += cp[1];
+                            }
+                            float* out = p.stat_partials + (int64_t)bi * 2 * p.N;
+                            out[j] = dot;
+                            out[p.N + j] = sq;
+                        }
                     }
                 }
             }
@@ -326,7 +368,7 @@ split_kernel(const float* __restrict__ in, int64_t ld_in, int rows, int cols, fl
 __global__ void __launch_bounds__(256)
 feedback_coef_kernel(const float* __restrict__ Hinv, int64_t ldh, const int32_t* __restrict__ blk_idx, int blk0, int b,
                      const int32_t* __restrict__ rem_idx, int rem0, int rem, float* __restrict__ hi,
-                     float* __restrict__ lo, int64_t ldb) {
+                     float* __restrict__ lo, int64_t ldb, float* __restrict__ csum_part) {
     __shared__ float tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int j0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
@@ -342,6 +384,13 @@ feedback_coef_kernel(const float* __restrict__ Hinv, int64_t ldh, const int32_t*
         tile[ii][tx] = v;
     }
     __syncthreads();
+    if (csum_part != nullptr && ty == 0) {
+        // sum over this CTA's 32 remaining positions of C[i, j], for its 32 block columns i (fixed order)
+        float s = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) s += tile[tx][jj];
+        if (i0 + tx < b) csum_part[(int64_t)blockIdx.x * b + i0 + tx] = s;
+    }
     for (int jj = ty; jj < 32; jj += 8) {
         const int j = j0 + jj, i = i0 + tx;
         if (j < rem && i < b) {
@@ -380,6 +429,28 @@ int gemm_operands_encode(GemmOperands* ops, const float* Ah, const float* Al, in
 // C (op)= A B' with pre-encoded operands; M, N <= the extents the operands were encoded with
 int launch_gemm_tf32x3_ops(int mode, float* C, int64_t ldc, int64_t M, int64_t N, const GemmOperands* ops,
                            const int32_t* col_idx, int64_t col0, cudaStream_t st) {
+    return launch_gemm_tf32x3_rows(mode, C, ldc, M, N, ops, 0, 0, col_idx, col0, st);
+}
+
+// as above, with A and B starting at rows a_row0 / b_row0 of the arrays the descriptors describe
+static int launch_gemm_impl(int mode, float* C, int64_t ldc, int64_t M, int64_t N, const GemmOperands* ops, int64_t a_row0,
+                            int64_t b_row0, const int32_t* col_idx, int64_t col0, const float* wbar, float* stat_partials,
+                            double* rowsum_next, cudaStream_t st);
+
+int launch_gemm_tf32x3_rows(int mode, float* C, int64_t ldc, int64_t M, int64_t N, const GemmOperands* ops,
+                            int64_t a_row0, int64_t b_row0, const int32_t* col_idx, int64_t col0, cudaStream_t st) {
+    return launch_gemm_impl(mode, C, ldc, M, N, ops, a_row0, b_row0, col_idx, col0, nullptr, nullptr, nullptr, st);
+}
+
+// error feedback with the next block's SSR statistics emitted from the epilogue
+int launch_gemm_feedback_stats(float* C, int64_t ldc, int64_t M, int64_t N, const GemmOperands* ops, const int32_t* col_idx,
+                               int64_t col0, const float* wbar, float* stat_partials, double* rowsum_next, cudaStream_t st) {
+    return launch_gemm_impl(GX_FEEDBACK, C, ldc, M, N, ops, 0, 0, col_idx, col0, wbar, stat_partials, rowsum_next, st);
+}
+
+static int launch_gemm_impl(int mode, float* C, int64_t ldc, int64_t M, int64_t N, const GemmOperands* ops, int64_t a_row0,
+                            int64_t b_row0, const int32_t* col_idx, int64_t col0, const float* wbar, float* stat_partials,
+                            double* rowsum_next, cudaStream_t st) {
     const int64_t K = ops->K;
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     GxProblem p;
@@ -389,6 +460,8 @@ int launch_gemm_tf32x3_ops(int mode, float* C, int64_t ldc, int64_t M, int64_t N
     p.mode = mode;
     p.C = C; p.ldc = ldc; p.col_idx = col_idx; p.col0 = (int)col0;
     p.k_chunk = (mode == GX_STORE_UPPER) ? 256 : 0;
+    p.a_row0 = (int)a_row0; p.b_row0 = (int)b_row0;
+    p.wbar = wbar; p.stat_partials = stat_partials; p.rowsum_next = rowsum_next;
     static const int dbg = []() { const char* e = getenv("TQ_GX_DEBUG"); return e ? atoi(e) : 0; }();
     p.debug = dbg;
     if (mode == GX_SUB_LOWER) {
@@ -424,9 +497,11 @@ int launch_gemm_tf32x3(int mode, float* C, int64_t ldc, int64_t M, int64_t N, in
 }
 
 int launch_feedback_coef(const float* Hinv, int64_t ldh, const int32_t* blk_idx, int64_t blk0, int64_t b,
-                         const int32_t* rem_idx, int64_t rem0, int64_t rem, float* ch, float* cl, int64_t ldb, cudaStream_t st) {
+                         const int32_t* rem_idx, int64_t rem0, int64_t rem, float* ch, float* cl, int64_t ldb,
+                         float* csum_part, cudaStream_t st) {
     dim3 grid((unsigned)ceil_div(rem, 32), (unsigned)ceil_div(b, 32));
-    feedback_coef_kernel<<<grid, 256, 0, st>>>(Hinv, ldh, blk_idx, (int)blk0, (int)b, rem_idx, (int)rem0, (int)rem, ch, cl, ldb);
+    feedback_coef_kernel<<<grid, 256, 0, st>>>(Hinv, ldh, blk_idx, (int)blk0, (int)b, rem_idx, (int)rem0, (int)rem, ch, cl, ldb,
+                                               csum_part);
     TQ_LAUNCH_CHECK("feedback_coef_kernel");
     return 0;
 }
@@ -440,7 +515,7 @@ int launch_err_feedback_tc(float* W, int64_t ldw, int64_t n, const float* Eh, co
     float* ch = coef_ws;
     float* cl = coef_ws + rem * ldb;
     int rc;
-    if ((rc = launch_feedback_coef(Hinv, ldh, blk_idx, blk0, b, rem_idx, rem0, rem, ch, cl, ldb, st))) return rc;
+    if ((rc = launch_feedback_coef(Hinv, ldh, blk_idx, blk0, b, rem_idx, rem0, rem, ch, cl, ldb, nullptr, st))) return rc;
     return launch_gemm_tf32x3(GX_FEEDBACK, W, ldw, n, rem, b, Eh, El, lde, ch, cl, ldb, rem_idx, rem0, st);
 }
 

@@ -20,7 +20,7 @@ constexpr int SEL_THREADS = 1024;
 
 __global__ void __launch_bounds__(256)
 ssr_rowmean_kernel(const float* __restrict__ W, int64_t ldw, int n, const int32_t* __restrict__ rem_idx, int rem,
-                   float* __restrict__ rowmean) {
+                   float* __restrict__ rowmean, double* __restrict__ rowsum) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= n) return;
@@ -35,7 +35,10 @@ ssr_rowmean_kernel(const float* __restrict__ W, int64_t ldw, int n, const int32_
     }
     for (; j < rem; j += 32) s0 += wrow[rem_idx[j]];
     const float s = warp_sum((s0 + s1) + (s2 + s3));
-    if (lane == 0) rowmean[row] = __fdiv_rn(s, (float)rem);
+    if (lane == 0) {
+        rowmean[row] = __fdiv_rn(s, (float)rem);
+        if (rowsum) rowsum[row] = (double)s;
+    }
 }
 
 // grid: (ceil(rem/128), num_chunks); 128 threads, thread = one remaining column, loops over the chunk's rows
@@ -109,43 +112,44 @@ __device__ int block_excl_scan_1024(int v, int* wsum, int* total) {
     return res;
 }
 
-__global__ void __launch_bounds__(SEL_THREADS)
-ssr_select_kernel(const float* __restrict__ partials, int num_chunks, const float* __restrict__ rowmean, int n,
-                  const float* __restrict__ wbar_sq_dev, const int32_t* __restrict__ rem_idx, int rem, int block,
-                  int32_t* __restrict__ blk_idx, int32_t* __restrict__ new_rem_idx, float* __restrict__ sims,
-                  uint32_t* __restrict__ keys /* scratch [rem] */) {
+// ||wbar||^2 in a fixed order (one CTA), reorder.py:55
+__global__ void __launch_bounds__(1024)
+ssr_wbarsq_kernel(const float* __restrict__ rowmean, int n, float* __restrict__ out) {
     __shared__ float red[32];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(rowmean[i], rowmean[i], s);
+    s = block_sum_1024(s, red);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+// similarities (reorder.py:56-59) and order-preserving keys, one thread per remaining column; the per-chunk
+// partials are folded in chunk order, so the result does not depend on the launch geometry
+__global__ void __launch_bounds__(256)
+ssr_sims_kernel(const float* __restrict__ partials, int num_chunks, const float* __restrict__ wbar_sq, int rem,
+                float* __restrict__ sims, uint32_t* __restrict__ keys) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= rem) return;
+    float dot = 0.f, sq = 0.f;
+    for (int c = 0; c < num_chunks; ++c) {
+        dot += partials[(int64_t)c * 2 * rem + j];
+        sq += partials[(int64_t)c * 2 * rem + rem + j];
+    }
+    const float mnorm = fmaxf(sqrtf(wbar_sq[0]), kTiny);
+    const float cn = fmaxf(sqrtf(sq), kTiny);
+    const float sim = __fdiv_rn(__fdiv_rn(dot, cn), mnorm);
+    sims[j] = sim;
+    keys[j] = order_key(sim);
+}
+
+__global__ void __launch_bounds__(SEL_THREADS)
+ssr_select_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ rem_idx, int rem, int block,
+                  int32_t* __restrict__ blk_idx, int32_t* __restrict__ new_rem_idx) {
     __shared__ int wsum[33];
     __shared__ int hist[256];
     __shared__ uint32_t s_prefix;
     __shared__ int s_need;
     __shared__ unsigned long long win[1024];   // selected (key, position), sorted at the end
     const int tid = threadIdx.x;
-
-    // ||wbar||, reorder.py:55
-    float msq;
-    if (wbar_sq_dev != nullptr) {
-        msq = wbar_sq_dev[0];
-    } else {
-        float s = 0.f;
-        for (int i = tid; i < n; i += SEL_THREADS) s = fmaf(rowmean[i], rowmean[i], s);
-        msq = block_sum_1024(s, red);
-    }
-    const float mnorm = fmaxf(sqrtf(msq), kTiny);
-
-    // similarities, reorder.py:56-59
-    for (int j = tid; j < rem; j += SEL_THREADS) {
-        float dot = 0.f, sq = 0.f;
-        for (int c = 0; c < num_chunks; ++c) {
-            dot += partials[(int64_t)c * 2 * rem + j];
-            sq += partials[(int64_t)c * 2 * rem + rem + j];
-        }
-        const float cn = fmaxf(sqrtf(sq), kTiny);
-        const float sim = __fdiv_rn(__fdiv_rn(dot, cn), mnorm);
-        if (sims) sims[j] = sim;
-        keys[j] = order_key(sim);
-    }
-    __syncthreads();
 
     // radix select: find the key of the block-th largest element, 8 bits at a time from the top
     uint32_t prefix = 0, pmask = 0;
@@ -260,8 +264,8 @@ int launch_ssr_fold(const float* partials, int64_t num_chunks, const float* rowm
 }
 
 int launch_ssr_stats(const float* W, int64_t ldw, int64_t n, const int32_t* rem_idx, int64_t rem, float* rowmean,
-                     float* partials, cudaStream_t st) {
-    ssr_rowmean_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, st>>>(W, ldw, (int)n, rem_idx, (int)rem, rowmean);
+                     float* partials, double* rowsum, cudaStream_t st) {
+    ssr_rowmean_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, st>>>(W, ldw, (int)n, rem_idx, (int)rem, rowmean, rowsum);
     TQ_LAUNCH_CHECK("ssr_rowmean_kernel");
     dim3 grid((unsigned)ceil_div(rem, SSR_COLS_PER_CTA), (unsigned)ceil_div(n, SSR_ROWS_PER_CHUNK));
     ssr_colstats_kernel<<<grid, SSR_COLS_PER_CTA, 0, st>>>(W, ldw, (int)n, rem_idx, (int)rem, rowmean, partials);
@@ -272,8 +276,16 @@ int launch_ssr_stats(const float* W, int64_t ldw, int64_t n, const int32_t* rem_
 int launch_ssr_select(const float* partials, int64_t num_chunks, const float* rowmean, int64_t n,
                       const float* wbar_sq_dev, const int32_t* rem_idx, int64_t rem, int64_t block,
                       int32_t* blk_idx, int32_t* new_rem_idx, float* sims, uint32_t* keys, cudaStream_t st) {
-    ssr_select_kernel<<<1, SEL_THREADS, 0, st>>>(partials, (int)num_chunks, rowmean, (int)n, wbar_sq_dev, rem_idx,
-                                                 (int)rem, (int)block, blk_idx, new_rem_idx, sims, keys);
+    // scratch for ||wbar||^2 sits behind the keys (callers size the sims array as 2*rem + 2 floats)
+    float* wsq = reinterpret_cast<float*>(keys + rem);
+    if (wbar_sq_dev == nullptr) {
+        ssr_wbarsq_kernel<<<1, 1024, 0, st>>>(rowmean, (int)n, wsq);
+        TQ_LAUNCH_CHECK("ssr_wbarsq_kernel");
+        wbar_sq_dev = wsq;
+    }
+    ssr_sims_kernel<<<(unsigned)ceil_div(rem, 256), 256, 0, st>>>(partials, (int)num_chunks, wbar_sq_dev, (int)rem, sims, keys);
+    TQ_LAUNCH_CHECK("ssr_sims_kernel");
+    ssr_select_kernel<<<1, SEL_THREADS, 0, st>>>(keys, rem_idx, (int)rem, (int)block, blk_idx, new_rem_idx);
     TQ_LAUNCH_CHECK("ssr_select_kernel");
     return 0;
 }
@@ -286,7 +298,7 @@ extern "C" int tq_ssr_stats(const float* W, int64_t ldw, int64_t n, const int32_
                             float* rowmean, float* partials, void* stream) {
     using namespace tq;
     TQ_CHECK_ARG(W && rem_idx && rowmean && partials && n > 0 && rem > 0, "tq_ssr_stats: bad arguments");
-    return launch_ssr_stats(W, ldw, n, rem_idx, rem, rowmean, partials, (cudaStream_t)stream);
+    return launch_ssr_stats(W, ldw, n, rem_idx, rem, rowmean, partials, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int tq_ssr_select(const float* partials, int64_t num_chunks, const float* rowmean, int64_t n,
@@ -298,7 +310,7 @@ extern "C" int tq_ssr_select(const float* partials, int64_t num_chunks, const fl
                  "tq_ssr_select: needs rem > block and block <= 1024; with rem <= block the block is the whole "
                  "remaining list (reorder.py:125-126)");
     TQ_CHECK_ARG(rowmean != nullptr || wbar_sq_dev != nullptr, "tq_ssr_select: need rowmean or wbar_sq_dev");
-    // the key scratch lives behind the sims array: callers give sims room for 2*rem floats
+    // the key scratch (and 2 floats for ||wbar||^2) live behind the sims array: callers give sims room for 2*rem + 2 floats
     return launch_ssr_select(partials, num_chunks, rowmean, n, wbar_sq_dev, rem_idx, rem, block, blk_idx,
                              new_rem_idx, sims, reinterpret_cast<uint32_t*>(sims + rem), (cudaStream_t)stream);
 }

@@ -2,25 +2,16 @@
 // enqueues every block step on the caller's stream with no host synchronisation -- the reference's
 // per-block syncs (`.tolist()` gptq.py:133, `torch.equal` quantizer.py:164, `.item()` quantizer.py:218)
 // are gone: the permutation, the remaining-column list and the AGA vector all stay on the device.
-#include "common.cuh"
-
-#include <cuda.h>
+#include "tc_common.cuh"
 
 namespace tq {
 
 int launch_atq_block(const float*, int64_t, int64_t, const int32_t*, int64_t, int64_t, const float*, int, int8_t*,
-                     int64_t, float*, float*, int64_t, float*, float*, int64_t, int32_t*, cudaStream_t);
-struct GemmOperands {
-    CUtensorMap ah, al, bh, bl;
-    int64_t K;
-};
-int gemm_operands_encode(GemmOperands*, const float*, const float*, int64_t, int64_t, const float*, const float*, int64_t,
-                         int64_t, int64_t);
-int launch_gemm_tf32x3_ops(int, float*, int64_t, int64_t, int64_t, const GemmOperands*, const int32_t*, int64_t, cudaStream_t);
-int launch_feedback_coef(const float*, int64_t, const int32_t*, int64_t, int64_t, const int32_t*, int64_t, int64_t, float*,
-                         float*, int64_t, cudaStream_t);
+                     int64_t, float*, float*, int64_t, float*, float*, int64_t, int32_t*, const double*, const double*, int64_t,
+                     float*, cudaStream_t);
+int launch_csum_fold(const float*, int64_t, int64_t, double*, cudaStream_t);
 int launch_aga_vector(const float*, int64_t, const int32_t*, int64_t, int64_t, int, float*, cudaStream_t);
-int launch_ssr_stats(const float*, int64_t, int64_t, const int32_t*, int64_t, float*, float*, cudaStream_t);
+int launch_ssr_stats(const float*, int64_t, int64_t, const int32_t*, int64_t, float*, float*, double*, cudaStream_t);
 int launch_ssr_select(const float*, int64_t, const float*, int64_t, const float*, const int32_t*, int64_t, int64_t,
                       int32_t*, int32_t*, float*, uint32_t*, cudaStream_t);
 int launch_err_feedback(float*, int64_t, int64_t, const float*, int64_t, const float*, int64_t, const int32_t*,
@@ -41,9 +32,12 @@ struct SweepWs {
     float* coef;       // [2][m][ldb] hi/lo coefficient operand of the feedback GEMM
     float* rowmean;
     float* partials;
-    float* sims;       // [2*m]: similarities + selection keys
+    float* sims;       // [2*m + 2]: similarities, selection keys, ||wbar||^2
     float* s1d;
     float* folded;     // [2*m + 1] all-reduced SSR statistics (row-sharded sweep)
+    double* rowsum[2]; // exact row sums over the remaining columns (current / being accumulated by the feedback epilogue)
+    double* csum;      // [block] row sums of the coefficient matrix C 1
+    float* csum_part;  // [ceil(m/32)][block] per-CTA partials of C 1
     int32_t* rem[2];
     int8_t* Tperm;
     int64_t bytes;
@@ -63,9 +57,13 @@ static SweepWs carve(void* base, int64_t n, int64_t m, int64_t block) {
     w.coef = reinterpret_cast<float*>(take(sizeof(float) * 2 * m * ldb));
     w.rowmean = reinterpret_cast<float*>(take(sizeof(float) * n));
     w.partials = reinterpret_cast<float*>(take(sizeof(float) * chunks * 2 * m));
-    w.sims = reinterpret_cast<float*>(take(sizeof(float) * 2 * m));
+    w.sims = reinterpret_cast<float*>(take(sizeof(float) * (2 * m + 2)));
     w.s1d = reinterpret_cast<float*>(take(sizeof(float) * (block + 1)));
     w.folded = reinterpret_cast<float*>(take(sizeof(float) * (2 * m + 1)));
+    w.rowsum[0] = reinterpret_cast<double*>(take(sizeof(double) * n));
+    w.rowsum[1] = reinterpret_cast<double*>(take(sizeof(double) * n));
+    w.csum = reinterpret_cast<double*>(take(sizeof(double) * block));
+    w.csum_part = reinterpret_cast<float*>(take(sizeof(float) * ((m + 31) / 32) * block));
     w.rem[0] = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * m));
     w.rem[1] = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * m));
     w.Tperm = reinterpret_cast<int8_t*>(take(n * m));
@@ -131,6 +129,13 @@ extern "C" int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const
             return rc;
     }
 
+    // SSR statistics: computed by two passes over W[:, rem] for the first block; afterwards (tensor-core feedback) the
+    // feedback GEMM's epilogue emits them for the columns it has just updated, from row means predicted exactly by the
+    // ATQ kernel (TQ_SWEEP_UNFUSED_STATS switches back to the two passes per block).
+    const bool fused_stats = tc_feedback && (flags & TQ_SWEEP_UNFUSED_STATS) == 0;
+    bool have_stats = false;              // ws.partials / ws.rowmean / ws.rowsum[rs] describe the current remaining set
+    int rs = 0;
+
     int cur = 0;
     int64_t done = 0, rem = m;
     for (int64_t k = 0; done < m; ++k) {
@@ -141,7 +146,8 @@ extern "C" int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const
             if (rem <= block) {                                   // reorder.py:125-126
                 TQ_CUDA(cudaMemcpyAsync(perm + done, ws.rem[cur], sizeof(int32_t) * rem, cudaMemcpyDeviceToDevice, st));
             } else {
-                if ((rc = launch_ssr_stats(W, ldw, n, ws.rem[cur], rem, ws.rowmean, ws.partials, st))) return rc;
+                if (!have_stats)
+                    if ((rc = launch_ssr_stats(W, ldw, n, ws.rem[cur], rem, ws.rowmean, ws.partials, ws.rowsum[rs], st))) return rc;
                 if (sharded) {
                     // rows are one shard of the layer: column statistics must cover every shard's rows
                     if ((rc = launch_ssr_fold(ws.partials, chunks, ws.rowmean, n, rem, ws.folded, st))) return rc;
@@ -165,22 +171,42 @@ extern "C" int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const
             blk_idx = contiguous ? nullptr : perm + done;
             rem_idx = contiguous ? nullptr : perm + done + b;
         }
+        // will the NEXT block be chosen by similarity?  then this step must leave statistics of the updated W behind
+        const bool emit_stats = fused_stats && order == TQ_ORDER_SSR && rem > block;
+        if (tc_feedback && rem > 0) {
+            if ((rc = launch_feedback_coef(Hinv, m, blk_idx, done, b, rem_idx, done + b, rem, coef_hi, coef_lo, ldb,
+                                           emit_stats ? ws.csum_part : nullptr, st)))
+                return rc;
+            if (emit_stats) {
+                if ((rc = launch_csum_fold(ws.csum_part, ceil_div(rem, 32), b, ws.csum, st))) return rc;
+                TQ_CUDA(cudaMemsetAsync(ws.rowsum[rs ^ 1], 0, sizeof(double) * n, st));
+            }
+        }
         const float* s1d = nullptr;
         if (aga != TQ_AGA_NONE) {
             if ((rc = launch_aga_vector(Haga, m, blk_idx, done, b, aga, ws.s1d, st))) return rc;
             s1d = ws.s1d;
         }
         if ((rc = launch_atq_block(W, ldw, n, blk_idx, done, b, s1d, max_iter, ws.Tperm + done, m, alpha + k, mu + k,
-                                   nb, ws.E, tc_feedback ? ws.E_lo : nullptr, ldb, nullptr, st)))
+                                   nb, ws.E, tc_feedback ? ws.E_lo : nullptr, ldb, nullptr,
+                                   emit_stats ? ws.rowsum[rs] : nullptr, emit_stats ? ws.csum : nullptr, rem,
+                                   emit_stats ? ws.rowmean : nullptr, st)))
             return rc;
+        have_stats = false;
         if (rem > 0) {                                            // gptq.py:170 (and SURVEY Q3)
             if (tc_feedback) {
-                if ((rc = launch_feedback_coef(Hinv, m, blk_idx, done, b, rem_idx, done + b, rem, coef_hi, coef_lo, ldb, st)))
-                    return rc;
-                rc = launch_gemm_tf32x3_ops(0 /* GX_FEEDBACK */, W, ldw, n, rem, (b == block) ? &ops_full : &ops_tail, rem_idx,
-                                            done + b, st);
-            } else
+                const GemmOperands* ops = (b == block) ? &ops_full : &ops_tail;
+                if (emit_stats) {
+                    rc = launch_gemm_feedback_stats(W, ldw, n, rem, ops, rem_idx, done + b, ws.rowmean, ws.partials,
+                                                    ws.rowsum[rs ^ 1], st);
+                    rs ^= 1;
+                    have_stats = true;
+                } else {
+                    rc = launch_gemm_tf32x3_ops(GX_FEEDBACK, W, ldw, n, rem, ops, rem_idx, done + b, st);
+                }
+            } else {
                 rc = launch_err_feedback(W, ldw, n, ws.E, ldb, Hinv, m, blk_idx, done, b, rem_idx, done + b, rem, st);
+            }
             if (rc) return rc;
         }
         done += b;

@@ -117,4 +117,33 @@ PFN_tmapEncodeTiled tmap_encode_fn();
 int make_tmap_2d(CUtensorMap* map, CUtensorMapDataType dt, int elem_bytes, const void* base, int64_t rows, int64_t cols,
                  int64_t ld, int box_rows, int box_cols, const char* what);
 
+
+// ---- split-TF32 GEMM (gemm_tc.cu): C (op)= A B' with A [M, K], B [N, K] K-major fp32 given as (hi, lo) pairs
+struct GemmOperands {
+    CUtensorMap ah, al, bh, bl;     // TMA descriptors of the four operand arrays
+    int64_t K;
+};
+enum GxMode {
+    GX_FEEDBACK = 0,      // all tiles; C[r, colmap(j)] -= acc
+    GX_SUB_LOWER = 1,     // tiles bi >= bj; C[r, c] -= acc for c <= r  (potrf trailing update)
+    GX_SUB_RECT = 2,      // all tiles; C[r, c] -= acc                  (trtri update)
+    GX_STORE_UPPER = 3    // tiles bi <= bj, K range starts at the tile's first column; C[r, c] = acc (lauum)
+};
+int gemm_operands_encode(GemmOperands* ops, const float* Ah, const float* Al, int64_t lda, int64_t Mmax, const float* Bh,
+                         const float* Bl, int64_t ldb, int64_t Nmax, int64_t K);
+int launch_gemm_tf32x3_rows(int mode, float* C, int64_t ldc, int64_t M, int64_t N, const GemmOperands* ops, int64_t a_row0,
+                            int64_t b_row0, const int32_t* col_idx, int64_t col0, cudaStream_t st);
+int launch_gemm_tf32x3_ops(int mode, float* C, int64_t ldc, int64_t M, int64_t N, const GemmOperands* ops,
+                           const int32_t* col_idx, int64_t col0, cudaStream_t st);
+int launch_gemm_tf32x3(int mode, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* Ah, const float* Al,
+                       int64_t lda, const float* Bh, const float* Bl, int64_t ldb, const int32_t* col_idx, int64_t col0,
+                       cudaStream_t st);
+int launch_split(const float* in, int64_t ld_in, int64_t rows, int64_t cols, float* hi, float* lo, int64_t ld_out,
+                 int transpose, cudaStream_t st);
+int launch_feedback_coef(const float* Hinv, int64_t ldh, const int32_t* blk_idx, int64_t blk0, int64_t b,
+                         const int32_t* rem_idx, int64_t rem0, int64_t rem, float* ch, float* cl, int64_t ldb,
+                         float* csum_part, cudaStream_t st);
+int launch_gemm_feedback_stats(float* C, int64_t ldc, int64_t M, int64_t N, const GemmOperands* ops, const int32_t* col_idx,
+                               int64_t col0, const float* wbar, float* stat_partials, double* rowsum_next, cudaStream_t st);
+
 }  // namespace tq

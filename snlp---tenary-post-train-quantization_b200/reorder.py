@@ -47,7 +47,7 @@ def _select(Wf, idx, block_size):
     k = min(block_size, rem - 1) if rem > 1 else 0
     blk = torch.empty(max(k, 1), dtype=torch.int32, device=Wf.device)
     new_rem = torch.empty(max(rem - k, 1), dtype=torch.int32, device=Wf.device)
-    sims = torch.empty(2 * rem, dtype=torch.float32, device=Wf.device)
+    sims = torch.empty(2 * rem + 2, dtype=torch.float32, device=Wf.device)
     with torch.cuda.device(Wf.device):
         _lib.check(lib.tq_ssr_select(_lib.ptr(partials), chunks, _lib.ptr(rowmean), n, None, _lib.ptr(idx), rem, k,
                                      _lib.ptr(blk), _lib.ptr(new_rem), _lib.ptr(sims), _lib.stream()),

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_size_queries_need_no_gpu():
     handle = _lib.load()
-    assert handle.tq_chol_workspace_floats(4096) == 4096 * 4096 + 32 * 128 * 128
+    assert handle.tq_chol_workspace_floats(4096) == 3 * 4096 * 4096 + 32 * 128 * 128   # L^-1, (hi, lo) splits, diagonal inverses
     assert handle.tq_ssr_num_chunks(4096) == 32
     assert handle.tq_sweep_workspace_bytes(4096, 4096, 128) > 4096 * 4096
 
