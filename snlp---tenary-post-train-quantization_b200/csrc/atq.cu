@@ -196,7 +196,7 @@ atq_block_kernel(const float* __restrict__ W, int64_t ldw, int n, const int32_t*
                  int b, const float* __restrict__ s1d, int max_iter, int8_t* __restrict__ T, int64_t ldt,
                  float* __restrict__ alpha_out, float* __restrict__ mu_out, int64_t ld_am,
                  float* __restrict__ E, float* __restrict__ E_lo, int64_t lde, int32_t* __restrict__ iters_out,
-                 const double* __restrict__ rowsum_cur, const double* __restrict__ csum, int rem_next,
+                 const float* __restrict__ rowsum_part, int rowsum_parts, const double* __restrict__ csum, int rem_next,
                  float* __restrict__ wbar_next) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -217,7 +217,9 @@ atq_block_kernel(const float* __restrict__ W, int64_t ldw, int n, const int32_t*
     if (wbar_next != nullptr) {
         // SSR bookkeeping for the NEXT selection: the row sum over the next remaining set, predicted exactly from
         // this block's removal and feedback:  sum_new = sum_cur - sum(W_b) - E . (C 1)   (gptq.py:186 summed over j)
-        double bs = 0.0, ec = 0.0;
+        double bs = 0.0, ec = 0.0, cursum = 0.0;
+        // current exact row sum = sum of the partials the previous feedback epilogue (or the first statistics pass) left
+        for (int t = lane; t < rowsum_parts; t += 32) cursum += (double)rowsum_part[(int64_t)t * n + row];
 #pragma unroll
         for (int e = 0; e < EPL; ++e) {
             if (r.valid[e]) {
@@ -230,8 +232,9 @@ atq_block_kernel(const float* __restrict__ W, int64_t ldw, int n, const int32_t*
         for (int o = 16; o > 0; o >>= 1) {
             bs += __shfl_xor_sync(0xffffffffu, bs, o);
             ec += __shfl_xor_sync(0xffffffffu, ec, o);
+            cursum += __shfl_xor_sync(0xffffffffu, cursum, o);
         }
-        if (lane == 0) wbar_next[row] = (float)((rowsum_cur[row] - bs - ec) / (double)rem_next);
+        if (lane == 0) wbar_next[row] = (float)((cursum - bs - ec) / (double)rem_next);
     }
     if (E != nullptr)
         r.store_error(E + (int64_t)row * lde, E_lo ? E_lo + (int64_t)row * lde : nullptr, b, alpha, mu,
@@ -279,35 +282,54 @@ atq_stage_kernel(int op, const float* __restrict__ W, int64_t ldw, int n, int b,
 // Hb'(Hb 1) is computed as Hb (Hb 1) with the same row-wise access.
 __global__ void __launch_bounds__(1024)
 aga_vector_kernel(const float* __restrict__ Hsrc, int64_t ldh, const int32_t* __restrict__ blk_idx, int col0,
-                  int b, int mode, float* __restrict__ s1d) {
+                  int b, int mode, float* __restrict__ s1d, const float* __restrict__ csum_part, int csum_parts,
+                  double* __restrict__ csum) {
     extern __shared__ float sh[];           // cols[b] (as int), u[b], s1[b]
     int* cols = reinterpret_cast<int*>(sh);
     float* u = sh + b;
     float* s1 = sh + 2 * b;
     __shared__ float red[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    // (independent of the AGA vector) fold the coefficient kernel's per-CTA partials of C 1 in a fixed order
+    if (csum != nullptr) {
+        for (int i = threadIdx.x; i < b; i += blockDim.x) {
+            double s = 0.0;
+            for (int t = 0; t < csum_parts; ++t) s += (double)csum_part[(int64_t)t * b + i];
+            csum[i] = s;
+        }
+    }
+    if (mode == TQ_AGA_NONE) return;
     for (int p = threadIdx.x; p < b; p += blockDim.x) cols[p] = blk_idx ? blk_idx[p] : col0 + p;
     __syncthreads();
-    for (int i = warp; i < b; i += nwarp) {
-        const float* hrow = Hsrc + (int64_t)cols[i] * ldh;
-        float s = 0.f;
-        for (int j = lane; j < b; j += 32) s += hrow[cols[j]];
-        s = warp_sum(s);
-        if (lane == 0) u[i] = s;             // row sums of the sub-block
-    }
-    __syncthreads();
-    if (mode == TQ_AGA_HESSIAN) {
-        for (int i = warp; i < b; i += nwarp) {
-            const float* hrow = Hsrc + (int64_t)cols[i] * ldh;
-            float s = 0.f;
-            for (int j = lane; j < b; j += 32) s = fmaf(hrow[cols[j]], u[j], s);
-            s = warp_sum(s);
-            if (lane == 0) s1[i] = s;        // Hb (Hb 1)
+    // row-times-vector products of the gathered sub-block; a warp owns rows warp, warp + nwarp, ... and issues the loads
+    // of all of them before reducing (b <= 512: at most 16 rows x 16 elements per lane, usually 4 x 4)
+    for (int phase = 0; phase < 2; ++phase) {
+        if (phase == 1 && mode != TQ_AGA_HESSIAN) break;
+        const float* vec = (phase == 0) ? nullptr : u;
+        float* out = (phase == 0) ? u : s1;
+        for (int i0 = warp; i0 < b; i0 += 4 * nwarp) {
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const int i = i0 + rr * nwarp;
+                if (i < b) {
+                    const float* hrow = Hsrc + (int64_t)cols[i] * ldh;
+                    for (int j = lane; j < b; j += 32) acc[rr] = vec ? fmaf(hrow[cols[j]], vec[j], acc[rr]) : acc[rr] + hrow[cols[j]];
+                }
+            }
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr) {
+                const float s = warp_sum(acc[rr]);
+                const int i = i0 + rr * nwarp;
+                if (lane == 0 && i < b) out[i] = s;
+            }
         }
-    } else {
-        for (int j = threadIdx.x; j < b; j += blockDim.x) s1[j] = u[j];
+        __syncthreads();
     }
-    __syncthreads();
+    if (mode != TQ_AGA_HESSIAN) {
+        for (int j = threadIdx.x; j < b; j += blockDim.x) s1[j] = u[j];
+        __syncthreads();
+    }
     float part = 0.f;
     for (int j = threadIdx.x; j < b; j += blockDim.x) {
         s1d[j] = s1[j];
@@ -323,32 +345,16 @@ aga_vector_kernel(const float* __restrict__ Hsrc, int64_t ldh, const int32_t* __
     }
 }
 
-// csum[i] = sum over all coefficient-kernel CTAs of their partial column sums, in a fixed order, in double
-__global__ void __launch_bounds__(128)
-csum_fold_kernel(const float* __restrict__ csum_part, int parts, int b, double* __restrict__ csum) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= b) return;
-    double s = 0.0;
-    for (int t = 0; t < parts; ++t) s += (double)csum_part[(int64_t)t * b + i];
-    csum[i] = s;
-}
-
-int launch_csum_fold(const float* csum_part, int64_t parts, int64_t b, double* csum, cudaStream_t st) {
-    csum_fold_kernel<<<(unsigned)ceil_div(b, 128), 128, 0, st>>>(csum_part, (int)parts, (int)b, csum);
-    TQ_LAUNCH_CHECK("csum_fold_kernel");
-    return 0;
-}
-
 int launch_atq_block(const float* W, int64_t ldw, int64_t n, const int32_t* blk_idx, int64_t col0, int64_t b,
                      const float* s1d, int max_iter, int8_t* T, int64_t ldt, float* alpha, float* mu,
-                     int64_t ld_am, float* E, float* E_lo, int64_t lde, int32_t* iters, const double* rowsum_cur,
-                     const double* csum, int64_t rem_next, float* wbar_next, cudaStream_t st) {
+                     int64_t ld_am, float* E, float* E_lo, int64_t lde, int32_t* iters, const float* rowsum_part,
+                     int64_t rowsum_parts, const double* csum, int64_t rem_next, float* wbar_next, cudaStream_t st) {
     const int warps = 8;
     dim3 grid((unsigned)ceil_div(n, warps)), block(warps * 32);
 #define TQ_ATQ_CASE(EPL)                                                                                      \
     atq_block_kernel<EPL><<<grid, block, 0, st>>>(W, ldw, (int)n, blk_idx, (int)col0, (int)b, s1d, max_iter, \
-                                                  T, ldt, alpha, mu, ld_am, E, E_lo, lde, iters, rowsum_cur, csum,     \
-                                                  (int)rem_next, wbar_next)
+                                                  T, ldt, alpha, mu, ld_am, E, E_lo, lde, iters, rowsum_part,          \
+                                                  (int)rowsum_parts, csum, (int)rem_next, wbar_next)
     if (b <= 32) TQ_ATQ_CASE(1);
     else if (b <= 64) TQ_ATQ_CASE(2);
     else if (b <= 128) TQ_ATQ_CASE(4);
@@ -359,9 +365,12 @@ int launch_atq_block(const float* W, int64_t ldw, int64_t n, const int32_t* blk_
     return 0;
 }
 
+// AGA vector of the block (mode HESSIAN / ACTIVATIONS) and/or the fold of the coefficient row sums (csum != NULL)
 int launch_aga_vector(const float* Hsrc, int64_t ldh, const int32_t* blk_idx, int64_t col0, int64_t b, int mode,
-                      float* s1d, cudaStream_t st) {
-    aga_vector_kernel<<<1, 1024, 3 * b * sizeof(float), st>>>(Hsrc, ldh, blk_idx, (int)col0, (int)b, mode, s1d);
+                      float* s1d, const float* csum_part, int64_t csum_parts, double* csum, cudaStream_t st) {
+    if (mode == TQ_AGA_NONE && csum == nullptr) return 0;
+    aga_vector_kernel<<<1, 1024, 3 * b * sizeof(float), st>>>(Hsrc, ldh, blk_idx, (int)col0, (int)b, mode, s1d, csum_part,
+                                                              (int)csum_parts, csum);
     TQ_LAUNCH_CHECK("aga_vector_kernel");
     return 0;
 }
@@ -377,7 +386,7 @@ extern "C" int tq_atq_block(const float* W, int64_t ldw, int64_t n, const int32_
                  (long long)n, (long long)b);
     TQ_CHECK_ARG(ldt >= b && ld_am >= 1 && (E == nullptr || lde >= b) && max_iter >= 0, "tq_atq_block: bad strides");
     return launch_atq_block(W, ldw, n, blk_idx, col0, b, s1d, max_iter, T, ldt, alpha, mu, ld_am, E, nullptr, lde, iters,
-                            nullptr, nullptr, 0, nullptr, (cudaStream_t)stream);
+                            nullptr, 0, nullptr, 0, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int tq_atq_stage(int op, const float* W, int64_t ldw, int64_t n, int64_t b, const int8_t* T_in,
@@ -410,5 +419,5 @@ extern "C" int tq_aga_vector(const float* Hsrc, int64_t ldh, const int32_t* blk_
     using namespace tq;
     TQ_CHECK_ARG(Hsrc && s1d && b > 0 && b <= 512, "tq_aga_vector: bad arguments");
     TQ_CHECK_ARG(mode == TQ_AGA_HESSIAN || mode == TQ_AGA_ACTIVATIONS, "tq_aga_vector: mode must be HESSIAN or ACTIVATIONS");
-    return launch_aga_vector(Hsrc, ldh, blk_idx, col0, b, mode, s1d, (cudaStream_t)stream);
+    return launch_aga_vector(Hsrc, ldh, blk_idx, col0, b, mode, s1d, nullptr, 0, nullptr, (cudaStream_t)stream);
 }

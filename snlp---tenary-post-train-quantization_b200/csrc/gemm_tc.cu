@@ -45,7 +45,7 @@ struct GxProblem {
     // C[r,j] * wbar[r] and C[r,j]^2 for every remaining position j, and exact row sums of the updated values
     const float* wbar;      // [M] predicted row means of the updated remaining columns
     float* stat_partials;   // [mt][2][N]
-    double* rowsum_next;    // [M], zeroed by the caller, accumulated with atomics
+    float* rowsum_part;     // [2*nt][M]: row sums of the updated values per (column tile, column half)
     int k_chunk;            // > 0: TMEM accumulates at most k_chunk of K at a time; chunks are summed in the
                             // smem C tile with round-to-nearest fp32 adds (the tensor core's accumulate truncates)
     int debug;              // development switch (env TQ_GX_DEBUG): 1 = drain accumulators only, 2 = no prefetch loads
@@ -257,7 +257,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
 #pragma unroll 8
                 for (int c = 0; c < 64; ++c)
                     if (jbase + c < p.N) rs += myrow[c];
-                if (r0 + lane < p.M) atomicAdd(p.rowsum_next + r0 + lane, (double)rs);
+                if (r0 + lane < p.M) p.rowsum_part[(int64_t)(bj * 2 + half) * p.M + r0 + lane] = rs;
             }
             __syncwarp();
             if (p.debug != 1) {
@@ -435,7 +435,7 @@ int launch_gemm_tf32x3_ops(int mode, float* C, int64_t ldc, int64_t M, int64_t N
 // as above, with A and B starting at rows a_row0 / b_row0 of the arrays the descriptors describe
 static int launch_gemm_impl(int mode, float* C, int64_t ldc, int64_t M, int64_t N, const GemmOperands* ops, int64_t a_row0,
                             int64_t b_row0, const int32_t* col_idx, int64_t col0, const float* wbar, float* stat_partials,
-                            double* rowsum_next, cudaStream_t st);
+                            float* rowsum_part, cudaStream_t st);
 
 int launch_gemm_tf32x3_rows(int mode, float* C, int64_t ldc, int64_t M, int64_t N, const GemmOperands* ops,
                             int64_t a_row0, int64_t b_row0, const int32_t* col_idx, int64_t col0, cudaStream_t st) {
@@ -444,13 +444,13 @@ int launch_gemm_tf32x3_rows(int mode, float* C, int64_t ldc, int64_t M, int64_t 
 
 // error feedback with the next block's SSR statistics emitted from the epilogue
 int launch_gemm_feedback_stats(float* C, int64_t ldc, int64_t M, int64_t N, const GemmOperands* ops, const int32_t* col_idx,
-                               int64_t col0, const float* wbar, float* stat_partials, double* rowsum_next, cudaStream_t st) {
-    return launch_gemm_impl(GX_FEEDBACK, C, ldc, M, N, ops, 0, 0, col_idx, col0, wbar, stat_partials, rowsum_next, st);
+                               int64_t col0, const float* wbar, float* stat_partials, float* rowsum_part, cudaStream_t st) {
+    return launch_gemm_impl(GX_FEEDBACK, C, ldc, M, N, ops, 0, 0, col_idx, col0, wbar, stat_partials, rowsum_part, st);
 }
 
 static int launch_gemm_impl(int mode, float* C, int64_t ldc, int64_t M, int64_t N, const GemmOperands* ops, int64_t a_row0,
                             int64_t b_row0, const int32_t* col_idx, int64_t col0, const float* wbar, float* stat_partials,
-                            double* rowsum_next, cudaStream_t st) {
+                            float* rowsum_part, cudaStream_t st) {
     const int64_t K = ops->K;
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     GxProblem p;
@@ -461,7 +461,7 @@ static int launch_gemm_impl(int mode, float* C, int64_t ldc, int64_t M, int64_t 
     p.C = C; p.ldc = ldc; p.col_idx = col_idx; p.col0 = (int)col0;
     p.k_chunk = (mode == GX_STORE_UPPER) ? 256 : 0;
     p.a_row0 = (int)a_row0; p.b_row0 = (int)b_row0;
-    p.wbar = wbar; p.stat_partials = stat_partials; p.rowsum_next = rowsum_next;
+    p.wbar = wbar; p.stat_partials = stat_partials; p.rowsum_part = rowsum_part;
     static const int dbg = []() { const char* e = getenv("TQ_GX_DEBUG"); return e ? atoi(e) : 0; }();
     p.debug = dbg;
     if (mode == GX_SUB_LOWER) {

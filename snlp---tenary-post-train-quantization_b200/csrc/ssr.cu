@@ -20,7 +20,7 @@ constexpr int SEL_THREADS = 1024;
 
 __global__ void __launch_bounds__(256)
 ssr_rowmean_kernel(const float* __restrict__ W, int64_t ldw, int n, const int32_t* __restrict__ rem_idx, int rem,
-                   float* __restrict__ rowmean, double* __restrict__ rowsum) {
+                   float* __restrict__ rowmean, float* __restrict__ rowsum) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= n) return;
@@ -37,7 +37,7 @@ ssr_rowmean_kernel(const float* __restrict__ W, int64_t ldw, int n, const int32_
     const float s = warp_sum((s0 + s1) + (s2 + s3));
     if (lane == 0) {
         rowmean[row] = __fdiv_rn(s, (float)rem);
-        if (rowsum) rowsum[row] = (double)s;
+        if (rowsum) rowsum[row] = s;            // the single row-sum partial the next ATQ kernel starts from
     }
 }
 
@@ -112,21 +112,30 @@ __device__ int block_excl_scan_1024(int v, int* wsum, int* total) {
     return res;
 }
 
-// ||wbar||^2 in a fixed order (one CTA), reorder.py:55
-__global__ void __launch_bounds__(1024)
-ssr_wbarsq_kernel(const float* __restrict__ rowmean, int n, float* __restrict__ out) {
-    __shared__ float red[32];
-    float s = 0.f;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(rowmean[i], rowmean[i], s);
-    s = block_sum_1024(s, red);
-    if (threadIdx.x == 0) out[0] = s;
-}
-
 // similarities (reorder.py:56-59) and order-preserving keys, one thread per remaining column; the per-chunk
 // partials are folded in chunk order, so the result does not depend on the launch geometry
 __global__ void __launch_bounds__(256)
-ssr_sims_kernel(const float* __restrict__ partials, int num_chunks, const float* __restrict__ wbar_sq, int rem,
-                float* __restrict__ sims, uint32_t* __restrict__ keys) {
+ssr_sims_kernel(const float* __restrict__ partials, int num_chunks, const float* __restrict__ wbar_sq,
+                const float* __restrict__ rowmean, int n, int rem, float* __restrict__ sims, uint32_t* __restrict__ keys) {
+    // ||wbar||^2 (reorder.py:55): taken from the caller (row-sharded sweep: all-reduced) or summed here, by every CTA
+    // in the same fixed order so all CTAs agree bit for bit
+    __shared__ float red[8];
+    __shared__ float s_msq;
+    if (wbar_sq == nullptr) {
+        float s = 0.f;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(rowmean[i], rowmean[i], s);
+        s = warp_sum(s);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float v = (threadIdx.x < 8) ? red[threadIdx.x] : 0.f;
+            v = warp_sum(v);
+            if (threadIdx.x == 0) s_msq = v;
+        }
+    } else if (threadIdx.x == 0) {
+        s_msq = wbar_sq[0];
+    }
+    __syncthreads();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= rem) return;
     float dot = 0.f, sq = 0.f;
@@ -134,7 +143,7 @@ ssr_sims_kernel(const float* __restrict__ partials, int num_chunks, const float*
         dot += partials[(int64_t)c * 2 * rem + j];
         sq += partials[(int64_t)c * 2 * rem + rem + j];
     }
-    const float mnorm = fmaxf(sqrtf(wbar_sq[0]), kTiny);
+    const float mnorm = fmaxf(sqrtf(s_msq), kTiny);
     const float cn = fmaxf(sqrtf(sq), kTiny);
     const float sim = __fdiv_rn(__fdiv_rn(dot, cn), mnorm);
     sims[j] = sim;
@@ -264,7 +273,7 @@ int launch_ssr_fold(const float* partials, int64_t num_chunks, const float* rowm
 }
 
 int launch_ssr_stats(const float* W, int64_t ldw, int64_t n, const int32_t* rem_idx, int64_t rem, float* rowmean,
-                     float* partials, double* rowsum, cudaStream_t st) {
+                     float* partials, float* rowsum, cudaStream_t st) {
     ssr_rowmean_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, st>>>(W, ldw, (int)n, rem_idx, (int)rem, rowmean, rowsum);
     TQ_LAUNCH_CHECK("ssr_rowmean_kernel");
     dim3 grid((unsigned)ceil_div(rem, SSR_COLS_PER_CTA), (unsigned)ceil_div(n, SSR_ROWS_PER_CHUNK));
@@ -276,14 +285,8 @@ int launch_ssr_stats(const float* W, int64_t ldw, int64_t n, const int32_t* rem_
 int launch_ssr_select(const float* partials, int64_t num_chunks, const float* rowmean, int64_t n,
                       const float* wbar_sq_dev, const int32_t* rem_idx, int64_t rem, int64_t block,
                       int32_t* blk_idx, int32_t* new_rem_idx, float* sims, uint32_t* keys, cudaStream_t st) {
-    // scratch for ||wbar||^2 sits behind the keys (callers size the sims array as 2*rem + 2 floats)
-    float* wsq = reinterpret_cast<float*>(keys + rem);
-    if (wbar_sq_dev == nullptr) {
-        ssr_wbarsq_kernel<<<1, 1024, 0, st>>>(rowmean, (int)n, wsq);
-        TQ_LAUNCH_CHECK("ssr_wbarsq_kernel");
-        wbar_sq_dev = wsq;
-    }
-    ssr_sims_kernel<<<(unsigned)ceil_div(rem, 256), 256, 0, st>>>(partials, (int)num_chunks, wbar_sq_dev, (int)rem, sims, keys);
+    ssr_sims_kernel<<<(unsigned)ceil_div(rem, 256), 256, 0, st>>>(partials, (int)num_chunks, wbar_sq_dev, rowmean, (int)n,
+                                                                   (int)rem, sims, keys);
     TQ_LAUNCH_CHECK("ssr_sims_kernel");
     ssr_select_kernel<<<1, SEL_THREADS, 0, st>>>(keys, rem_idx, (int)rem, (int)block, blk_idx, new_rem_idx);
     TQ_LAUNCH_CHECK("ssr_select_kernel");

@@ -7,11 +7,11 @@
 namespace tq {
 
 int launch_atq_block(const float*, int64_t, int64_t, const int32_t*, int64_t, int64_t, const float*, int, int8_t*,
-                     int64_t, float*, float*, int64_t, float*, float*, int64_t, int32_t*, const double*, const double*, int64_t,
-                     float*, cudaStream_t);
-int launch_csum_fold(const float*, int64_t, int64_t, double*, cudaStream_t);
-int launch_aga_vector(const float*, int64_t, const int32_t*, int64_t, int64_t, int, float*, cudaStream_t);
-int launch_ssr_stats(const float*, int64_t, int64_t, const int32_t*, int64_t, float*, float*, double*, cudaStream_t);
+                     int64_t, float*, float*, int64_t, float*, float*, int64_t, int32_t*, const float*, int64_t, const double*,
+                     int64_t, float*, cudaStream_t);
+int launch_aga_vector(const float*, int64_t, const int32_t*, int64_t, int64_t, int, float*, const float*, int64_t, double*,
+                      cudaStream_t);
+int launch_ssr_stats(const float*, int64_t, int64_t, const int32_t*, int64_t, float*, float*, float*, cudaStream_t);
 int launch_ssr_select(const float*, int64_t, const float*, int64_t, const float*, const int32_t*, int64_t, int64_t,
                       int32_t*, int32_t*, float*, uint32_t*, cudaStream_t);
 int launch_err_feedback(float*, int64_t, int64_t, const float*, int64_t, const float*, int64_t, const int32_t*,
@@ -35,7 +35,8 @@ struct SweepWs {
     float* sims;       // [2*m + 2]: similarities, selection keys, ||wbar||^2
     float* s1d;
     float* folded;     // [2*m + 1] all-reduced SSR statistics (row-sharded sweep)
-    double* rowsum[2]; // exact row sums over the remaining columns (current / being accumulated by the feedback epilogue)
+    float* rowsum_part[2]; // [2*ceil(m/128)][n] row-sum partials over the remaining columns (read by ATQ / written by the
+                           // feedback epilogue)
     double* csum;      // [block] row sums of the coefficient matrix C 1
     float* csum_part;  // [ceil(m/32)][block] per-CTA partials of C 1
     int32_t* rem[2];
@@ -60,8 +61,8 @@ static SweepWs carve(void* base, int64_t n, int64_t m, int64_t block) {
     w.sims = reinterpret_cast<float*>(take(sizeof(float) * (2 * m + 2)));
     w.s1d = reinterpret_cast<float*>(take(sizeof(float) * (block + 1)));
     w.folded = reinterpret_cast<float*>(take(sizeof(float) * (2 * m + 1)));
-    w.rowsum[0] = reinterpret_cast<double*>(take(sizeof(double) * n));
-    w.rowsum[1] = reinterpret_cast<double*>(take(sizeof(double) * n));
+    w.rowsum_part[0] = reinterpret_cast<float*>(take(sizeof(float) * 2 * ((m + 127) / 128) * n));
+    w.rowsum_part[1] = reinterpret_cast<float*>(take(sizeof(float) * 2 * ((m + 127) / 128) * n));
     w.csum = reinterpret_cast<double*>(take(sizeof(double) * block));
     w.csum_part = reinterpret_cast<float*>(take(sizeof(float) * ((m + 31) / 32) * block));
     w.rem[0] = reinterpret_cast<int32_t*>(take(sizeof(int32_t) * m));
@@ -133,8 +134,9 @@ extern "C" int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const
     // feedback GEMM's epilogue emits them for the columns it has just updated, from row means predicted exactly by the
     // ATQ kernel (TQ_SWEEP_UNFUSED_STATS switches back to the two passes per block).
     const bool fused_stats = tc_feedback && (flags & TQ_SWEEP_UNFUSED_STATS) == 0;
-    bool have_stats = false;              // ws.partials / ws.rowmean / ws.rowsum[rs] describe the current remaining set
+    bool have_stats = false;              // ws.partials / ws.rowmean / ws.rowsum_part[rs] describe the current remaining set
     int rs = 0;
+    int64_t rs_parts = 1;                 // number of row-sum partials in ws.rowsum_part[rs]
 
     int cur = 0;
     int64_t done = 0, rem = m;
@@ -146,8 +148,10 @@ extern "C" int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const
             if (rem <= block) {                                   // reorder.py:125-126
                 TQ_CUDA(cudaMemcpyAsync(perm + done, ws.rem[cur], sizeof(int32_t) * rem, cudaMemcpyDeviceToDevice, st));
             } else {
-                if (!have_stats)
-                    if ((rc = launch_ssr_stats(W, ldw, n, ws.rem[cur], rem, ws.rowmean, ws.partials, ws.rowsum[rs], st))) return rc;
+                if (!have_stats) {
+                    if ((rc = launch_ssr_stats(W, ldw, n, ws.rem[cur], rem, ws.rowmean, ws.partials, ws.rowsum_part[rs], st))) return rc;
+                    rs_parts = 1;
+                }
                 if (sharded) {
                     // rows are one shard of the layer: column statistics must cover every shard's rows
                     if ((rc = launch_ssr_fold(ws.partials, chunks, ws.rowmean, n, rem, ws.folded, st))) return rc;
@@ -177,19 +181,14 @@ extern "C" int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const
             if ((rc = launch_feedback_coef(Hinv, m, blk_idx, done, b, rem_idx, done + b, rem, coef_hi, coef_lo, ldb,
                                            emit_stats ? ws.csum_part : nullptr, st)))
                 return rc;
-            if (emit_stats) {
-                if ((rc = launch_csum_fold(ws.csum_part, ceil_div(rem, 32), b, ws.csum, st))) return rc;
-                TQ_CUDA(cudaMemsetAsync(ws.rowsum[rs ^ 1], 0, sizeof(double) * n, st));
-            }
         }
-        const float* s1d = nullptr;
-        if (aga != TQ_AGA_NONE) {
-            if ((rc = launch_aga_vector(Haga, m, blk_idx, done, b, aga, ws.s1d, st))) return rc;
-            s1d = ws.s1d;
-        }
+        const float* s1d = (aga != TQ_AGA_NONE) ? ws.s1d : nullptr;
+        if ((rc = launch_aga_vector(Haga, m, blk_idx, done, b, aga, ws.s1d, emit_stats ? ws.csum_part : nullptr,
+                                    ceil_div(rem, 32), emit_stats ? ws.csum : nullptr, st)))
+            return rc;
         if ((rc = launch_atq_block(W, ldw, n, blk_idx, done, b, s1d, max_iter, ws.Tperm + done, m, alpha + k, mu + k,
                                    nb, ws.E, tc_feedback ? ws.E_lo : nullptr, ldb, nullptr,
-                                   emit_stats ? ws.rowsum[rs] : nullptr, emit_stats ? ws.csum : nullptr, rem,
+                                   emit_stats ? ws.rowsum_part[rs] : nullptr, rs_parts, emit_stats ? ws.csum : nullptr, rem,
                                    emit_stats ? ws.rowmean : nullptr, st)))
             return rc;
         have_stats = false;
@@ -198,8 +197,9 @@ extern "C" int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const
                 const GemmOperands* ops = (b == block) ? &ops_full : &ops_tail;
                 if (emit_stats) {
                     rc = launch_gemm_feedback_stats(W, ldw, n, rem, ops, rem_idx, done + b, ws.rowmean, ws.partials,
-                                                    ws.rowsum[rs ^ 1], st);
+                                                    ws.rowsum_part[rs ^ 1], st);
                     rs ^= 1;
+                    rs_parts = 2 * ceil_div(rem, 128);
                     have_stats = true;
                 } else {
                     rc = launch_gemm_tf32x3_ops(GX_FEEDBACK, W, ldw, n, rem, ops, rem_idx, done + b, st);

@@ -144,6 +144,6 @@ int launch_feedback_coef(const float* Hinv, int64_t ldh, const int32_t* blk_idx,
                          const int32_t* rem_idx, int64_t rem0, int64_t rem, float* ch, float* cl, int64_t ldb,
                          float* csum_part, cudaStream_t st);
 int launch_gemm_feedback_stats(float* C, int64_t ldc, int64_t M, int64_t N, const GemmOperands* ops, const int32_t* col_idx,
-                               int64_t col0, const float* wbar, float* stat_partials, double* rowsum_next, cudaStream_t st);
+                               int64_t col0, const float* wbar, float* stat_partials, float* rowsum_part, cudaStream_t st);
 
 }  // namespace tq
