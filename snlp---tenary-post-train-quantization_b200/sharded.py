@@ -129,9 +129,10 @@ class ShardedLayer:
 
     def quantize(self, linears, use_ssr: bool = True, aga: str = "hessian", max_iter: int = 100, hess_timing=None):
         """linears: [(name, W (n, m) replicated on every rank, X_local (this rank's samples, (.., m)))].
-        Returns [(name, alpha_slab, mu_slab, T_int8_slab, perm, (row_lo, row_hi))].
+        Returns [(name, alpha_slab, mu_slab, T_int8_slab, perm, (row_lo, row_hi))] in the input order.
         hess_timing: optional list that receives (start_event, end_event, tokens, m) per Hessian launch."""
         ctx = self.ctx
+        main = torch.cuda.current_stream(ctx.device)
         states = []
         for _, W, X in linears:
             st = HessianState(W.shape[1], W.device)
@@ -143,6 +144,9 @@ class ShardedLayer:
                 e1.record()
                 hess_timing.append((e0, e1, X.numel() // X.shape[-1], W.shape[1]))
             states.append(st)
+        # cheapest inverses first: their sweeps then run while the widest inverse is still being computed on its owner
+        order = sorted(range(len(linears)), key=lambda i: states[i].columns)
+        pending = {}
         if ctx.world > 1:
             counts = torch.tensor([st.nsamples for st in states], dtype=torch.int64, device=ctx.device)
             dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=ctx.group)
@@ -150,28 +154,42 @@ class ShardedLayer:
                 dist.all_reduce(st.H, op=dist.ReduceOp.SUM, group=ctx.group)
                 st.nsamples = int(c)
                 st._cache.clear()
-            # inverses: owner computes, everyone receives
-            pending = []
-            for i, st in enumerate(states):
-                owner = i % ctx.world
+            # inverses are dealt to the ranks and computed on a side stream of their owner
+            if not hasattr(self, "_inv_stream"):
+                self._inv_stream = torch.cuda.Stream(ctx.device)
+            self._inv_stream.wait_stream(main)
+            for slot, i in enumerate(order):
+                st = states[i]
+                owner = slot % ctx.world
                 m = st.columns
                 if owner == ctx.rank:
-                    Hd, Hinv, info = st.damped_inverse(self.percdamp)
+                    with torch.cuda.stream(self._inv_stream):
+                        Hd, Hinv, info = st.damped_inverse(self.percdamp)
+                        done = torch.cuda.Event()
+                        done.record(self._inv_stream)
                 else:
                     Hd = st.damped(self.percdamp)
                     Hinv = torch.empty((m, m), dtype=torch.float32, device=ctx.device)
                     info = torch.zeros(1, dtype=torch.int32, device=ctx.device)
-                pending.append((st, owner, Hd, Hinv, info))
-            for st, owner, Hd, Hinv, info in pending:
+                    done = None
+                pending[i] = (owner, Hd, Hinv, info, done)
+        out = [None] * len(linears)
+        for i in order:
+            name, W, _ = linears[i]
+            st = states[i]
+            if ctx.world > 1:
+                owner, Hd, Hinv, info, done = pending[i]
+                if done is not None:
+                    main.wait_event(done)                       # only this inverse, not the owner's later ones
+                    for t in (Hd, Hinv, info):
+                        t.record_stream(main)
                 dist.broadcast(Hinv, src=owner, group=ctx.group)
                 dist.broadcast(info, src=owner, group=ctx.group)
                 st._cache[float(self.percdamp)] = (Hd, Hinv, info)
-        out = []
-        for (name, W, _), st in zip(linears, states):
             lo, hi = ctx.row_range(W.shape[0])
             g = GPTQ(LinearView(W[lo:hi]), self.block_size, self.percdamp, hessian=st)
             if ctx.world > 1:
                 g.sweep_flags = _lib.SWEEP_ROW_SHARD
             alpha, mu, _, perm = g.quantize(use_ssr=use_ssr, aga=aga, max_iter=max_iter)
-            out.append((name, alpha, mu, g.T_int8, perm, (lo, hi)))
+            out[i] = (name, alpha, mu, g.T_int8, perm, (lo, hi))
         return out
