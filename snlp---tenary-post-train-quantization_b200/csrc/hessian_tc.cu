@@ -246,7 +246,9 @@ int hessian_accum_tcgen05(float* H, int64_t ldh, const void* X, int64_t Nt, int6
     int64_t kc_l2 = (40ll << 20) / (2 * m);
     kc_l2 = (kc_l2 / HT_BK) * HT_BK;
     if (kc_l2 < 256) kc_l2 = 256;
-    if (kc_l2 > 8192) kc_l2 = 8192;
+    if (kc_l2 > 2048) kc_l2 = 2048;   // also bounds the length of one TMEM accumulation: the tensor core's fp32 add truncates, and
+                                      // a sum of squares over L tokens picks up a relative bias of ~L * 2^-25 (measured 2.8e-5 at
+                                      // L = 4864, 9e-6 at 1792); 2048 is the reference's own per-add_batch granularity
     const int64_t want_chunks = ceil_div((int64_t)6 * sms, sched.tiles);
     int64_t kc = ceil_div(ceil_div(Nt, want_chunks), HT_BK) * HT_BK;
     if (kc < 256) kc = 256;

@@ -44,7 +44,8 @@ def test_full_size_layer_properties(n, m, order):
     assert torch.equal(H, H.T)
     Xd = X.double()
     tr = torch.diagonal(H).double().sum().item()
-    assert abs(tr - (Xd * Xd).sum().item()) <= 1e-6 * tr
+    tr_err = abs(tr - (Xd * Xd).sum().item()) / tr        # fp32 accumulation of 262144 products per entry
+    assert tr_err <= 2e-5, tr_err
     ones = torch.ones(m, dtype=torch.float64, device=DEV)
     ref = Xd.T @ (Xd @ ones)
     got = H.double() @ ones
@@ -86,7 +87,7 @@ def test_full_size_layer_properties(n, m, order):
     packed, shape = tq100.pack_ternary(q.T_int8)
     assert packed.numel() == (n * m + 3) // 4
     assert torch.equal(tq100.unpack_ternary(packed, shape), q.T_int8)
-    print(f"{n}x{m} {order}: recon {err:.4f}, inverse probe residual {resid:.2e}")
+    print(f"{n}x{m} {order}: recon {err:.4f}, inverse probe residual {resid:.2e}, trace rel err {tr_err:.2e}")
 
 
 @pytest.mark.parametrize("name,n,m", [("q_proj", 768, 768), ("fc1", 3072, 768), ("fc2", 768, 3072)])
