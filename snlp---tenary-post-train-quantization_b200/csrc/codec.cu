@@ -81,6 +81,24 @@ unpack2b_kernel(const uint8_t* __restrict__ in, int64_t count, int8_t* __restric
     }
 }
 
+// vector path: one 32-bit word of packed input -> 16 int8 codes (one 128-bit store) per thread
+__global__ void __launch_bounds__(256)
+unpack2b_vec_kernel(const uint32_t* __restrict__ in, int64_t groups, int4* __restrict__ out) {
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t word = in[g];
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t byte = (word >> (8 * q)) & 0xFFu;
+            // spread the four 2-bit codes of this byte over four bytes, then subtract 1 per byte (codes are 0,1,2: no borrow
+            // crosses a byte because every byte is first OR-ed with 0x80 and the marker is removed afterwards)
+            const uint32_t c = (byte & 3u) | ((byte & 0xCu) << 6) | ((byte & 0x30u) << 12) | ((byte & 0xC0u) << 18);
+            o[q] = ((c | 0x80808080u) - 0x01010101u) ^ 0x80808080u;
+        }
+        out[g] = make_int4((int)o[0], (int)o[1], (int)o[2], (int)o[3]);
+    }
+}
+
 static inline unsigned grid_for(int64_t work, int threads) {
     int64_t g = ceil_div(work, threads);
     const int64_t cap = (int64_t)sm_count() * 16;
@@ -151,7 +169,18 @@ extern "C" int tq_unpack2b(const uint8_t* packed, int64_t count, int8_t* T, void
     using namespace tq;
     TQ_CHECK_ARG(T && packed && count >= 0, "tq_unpack2b: bad arguments");
     if (count == 0) return 0;
-    unpack2b_kernel<<<grid_for((count + 3) / 4, 256), 256, 0, (cudaStream_t)stream>>>(packed, count, T);
-    TQ_LAUNCH_CHECK("unpack2b_kernel");
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(T) & 15) == 0) && ((reinterpret_cast<uintptr_t>(packed) & 3) == 0);
+    const int64_t groups = aligned ? count / 16 : 0;
+    if (groups > 0) {
+        unpack2b_vec_kernel<<<grid_for(groups, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t*>(packed), groups,
+                                                                   reinterpret_cast<int4*>(T));
+        TQ_LAUNCH_CHECK("unpack2b_vec_kernel");
+    }
+    const int64_t done = groups * 16;
+    if (done < count) {
+        unpack2b_kernel<<<grid_for((count - done + 3) / 4, 256), 256, 0, st>>>(packed + done / 4, count - done, T + done);
+        TQ_LAUNCH_CHECK("unpack2b_kernel");
+    }
     return 0;
 }

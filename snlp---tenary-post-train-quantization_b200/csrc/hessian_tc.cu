@@ -10,8 +10,7 @@
 //   epilogue  : tcgen05.ld 32 columns -> swizzled smem -> TMA reduce-add (fp32 add in L2) into H;
 //               this is the reference's `H +=`, and it lets several token chunks of one tile be
 //               in flight on different SMs with no ordering between them
-//   schedule  : persistent, one CTA per SM; work item = (token chunk, tile), chunk-major so that the
-//               X rows of the current chunk (<= ~40 MB) stay L2-resident while all tiles consume them;
+//   schedule  : persistent, one CTA per SM; work item = (group of tiles, token chunk, tile): see TileSched;
 //               only tiles that touch the upper triangle are computed (tq_symmetrize mirrors later)
 //   roles     : warp 0 TMA producer, warp 1 MMA issuer (one thread), warp 2 TMEM allocator,
 //               warps 4-7 epilogue (TMEM lane quarter = warp % 4)
@@ -37,23 +36,59 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
            (1ull << 46) | (2ull << 61);
 }
 
+// Work schedule.  Tiles (128 rows x 256 cols of H) that touch the upper triangle are bundled into square GROUPS of
+// 28 x 14 tiles (3584 x 3584 of H, <= 49 MB): a group's tiles stay L2-resident while ALL token chunks are streamed
+// through it, so the per-chunk TMA reduce-adds hit L2 instead of DRAM (for m > ~4600 the whole H does not fit and a
+// plain chunk-major sweep turns every reduce into a DRAM read-modify-write).  Inside a group: chunk-major, tile-minor,
+// so the chunk's rows of X for the group's columns (<= 29 MB) are fetched from DRAM once per group.
+constexpr int HT_GI = 28, HT_GJ = 14, HT_MAX_GROUPS = 136;
+
 struct TileSched {
-    int nbi, nbj, tiles;
-    __device__ __forceinline__ void decode(int t, int& bi, int& bj) const {
-        int j = 0;
-        for (;; ++j) {
-            const int cnt = min(nbi, 2 * j + 2);      // row blocks of column block j that touch the upper triangle
+    int nbi, nbj, gdim, ngroups, num_chunks;
+    int tile_prefix[HT_MAX_GROUPS + 1];   // tiles in groups [0, g)
+
+    __host__ __device__ static int tiles_in_col(int bj, int bi0, int bi1) {   // valid bi in [bi0, bi1): bi <= 2*bj + 1
+        const int hi = (2 * bj + 2 < bi1) ? 2 * bj + 2 : bi1;
+        return hi > bi0 ? hi - bi0 : 0;
+    }
+    __host__ __device__ void group_rect(int g, int& bi0, int& bi1, int& bj0, int& bj1) const {
+        // groups enumerated over the upper triangle of the gdim x gdim group grid: (gi <= gj), gj-major
+        int gj = 0, rem = g;
+        while (rem > gj) { rem -= gj + 1; ++gj; }
+        const int gi = rem;
+        bi0 = gi * HT_GI; bi1 = (bi0 + HT_GI < nbi) ? bi0 + HT_GI : nbi;
+        bj0 = gj * HT_GJ; bj1 = (bj0 + HT_GJ < nbj) ? bj0 + HT_GJ : nbj;
+    }
+    __host__ __device__ int group_tiles(int g) const {
+        int bi0, bi1, bj0, bj1, n = 0;
+        group_rect(g, bi0, bi1, bj0, bj1);
+        for (int bj = bj0; bj < bj1; ++bj) n += tiles_in_col(bj, bi0, bi1);
+        return n;
+    }
+    __device__ __forceinline__ long long total_items() const { return (long long)tile_prefix[ngroups] * num_chunks; }
+    // item -> (chunk, bi, bj)
+    __device__ __forceinline__ void decode(long long it, int& chunk, int& bi, int& bj) const {
+        int g = 0;
+        while ((long long)tile_prefix[g + 1] * num_chunks <= it) ++g;
+        const int tg = tile_prefix[g + 1] - tile_prefix[g];
+        const long long local = it - (long long)tile_prefix[g] * num_chunks;
+        chunk = (int)(local / tg);
+        int t = (int)(local - (long long)chunk * tg);
+        int bi0, bi1, bj0, bj1;
+        group_rect(g, bi0, bi1, bj0, bj1);
+        bj = bj0;
+        for (;; ++bj) {
+            const int cnt = tiles_in_col(bj, bi0, bi1);
             if (t < cnt) break;
             t -= cnt;
         }
-        bi = t;
-        bj = j;
+        bi = bi0 + t;
     }
 };
 
 __global__ void __launch_bounds__(HT_THREADS, 1)
 hessian_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_h,
-                  int Nt, int kc, int num_chunks, TileSched sched, uint32_t idesc) {
+                  int Nt, int kc, const __grid_constant__ TileSched sched, uint32_t idesc) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t s_base = smem_u32(smem);
@@ -84,15 +119,14 @@ hessian_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int total_items = num_chunks * sched.tiles;
+    const long long total_items = sched.total_items();
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
         int stage = 0, phase = 0;
-        for (int it = blockIdx.x; it < total_items; it += gridDim.x) {
-            const int chunk = it / sched.tiles;
-            int bi, bj;
-            sched.decode(it - chunk * sched.tiles, bi, bj);
+        for (long long it = blockIdx.x; it < total_items; it += gridDim.x) {
+            int chunk, bi, bj;
+            sched.decode(it, chunk, bi, bj);
             const int t0 = chunk * kc;
             const int t1 = min(Nt, t0 + kc);
             const int nkb = (t1 - t0 + HT_BK - 1) / HT_BK;
@@ -112,8 +146,9 @@ hessian_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
         int stage = 0, phase = 0, n_item = 0;
-        for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++n_item) {
-            const int chunk = it / sched.tiles;
+        for (long long it = blockIdx.x; it < total_items; it += gridDim.x, ++n_item) {
+            int chunk, bi, bj;
+            sched.decode(it, chunk, bi, bj);
             const int t0 = chunk * kc;
             const int t1 = min(Nt, t0 + kc);
             const int nkb = (t1 - t0 + HT_BK - 1) / HT_BK;
@@ -143,10 +178,9 @@ hessian_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         const int row = q * 32 + lane;                   // row of the 128-row tile
         const bool leader = (warp == 4 && lane == 0);
         int n_item = 0, estage = 0;
-        for (int it = blockIdx.x; it < total_items; it += gridDim.x, ++n_item) {
-            const int chunk = it / sched.tiles;
-            int bi, bj;
-            sched.decode(it - chunk * sched.tiles, bi, bj);
+        for (long long it = blockIdx.x; it < total_items; it += gridDim.x, ++n_item) {
+            int chunk, bi, bj;
+            sched.decode(it, chunk, bi, bj);
             const int acc = n_item & 1;
             mbar_wait(tfull_bar(acc), (n_item >> 1) & 1);
             tc_fence_after();
@@ -237,25 +271,30 @@ int hessian_accum_tcgen05(float* H, int64_t ldh, const void* X, int64_t Nt, int6
     TileSched sched;
     sched.nbi = (int)ceil_div(m, HT_BM);
     sched.nbj = (int)ceil_div(m, HT_BN);
-    sched.tiles = 0;
-    for (int j = 0; j < sched.nbj; ++j) sched.tiles += (sched.nbi < 2 * j + 2) ? sched.nbi : 2 * j + 2;
+    sched.gdim = (int)ceil_div(sched.nbj, HT_GJ);
+    sched.ngroups = sched.gdim * (sched.gdim + 1) / 2;
+    TQ_CHECK_ARG(sched.ngroups <= HT_MAX_GROUPS, "tq_hessian_accum: m = %lld is beyond the scheduler's group table", (long long)m);
+    sched.tile_prefix[0] = 0;
+    for (int g = 0; g < sched.ngroups; ++g) sched.tile_prefix[g + 1] = sched.tile_prefix[g] + sched.group_tiles(g);
+    const int64_t tiles = sched.tile_prefix[sched.ngroups];
+    const int64_t tiles_per_group = tiles / sched.ngroups > 0 ? tiles / sched.ngroups : 1;
 
-    // token chunk: small enough that chunk x m x 2 B stays L2-resident while every tile reads it,
-    // large enough to amortise the reduce-add epilogue, and giving >= ~6 work items per SM
+    // token chunk = one TMEM accumulation: small enough that the group's slab of X (chunk x <= 7168 cols x 2 B) plus the
+    // group's H tiles stay L2-resident, capped at 2048 tokens (see below), and giving >= ~6 work items per SM
     const int sms = sm_count();
-    int64_t kc_l2 = (40ll << 20) / (2 * m);
+    int64_t kc_l2 = (40ll << 20) / (2 * (m < 7168 ? m : 7168));
     kc_l2 = (kc_l2 / HT_BK) * HT_BK;
     if (kc_l2 < 256) kc_l2 = 256;
     if (kc_l2 > 2048) kc_l2 = 2048;   // also bounds the length of one TMEM accumulation: the tensor core's fp32 add truncates, and
                                       // a sum of squares over L tokens picks up a relative bias of ~L * 2^-25 (measured 2.8e-5 at
                                       // L = 4864, 9e-6 at 1792); 2048 is the reference's own per-add_batch granularity
-    const int64_t want_chunks = ceil_div((int64_t)6 * sms, sched.tiles);
+    const int64_t want_chunks = ceil_div((int64_t)6 * sms, tiles_per_group);
     int64_t kc = ceil_div(ceil_div(Nt, want_chunks), HT_BK) * HT_BK;
     if (kc < 256) kc = 256;
     if (kc > kc_l2) kc = kc_l2;
     const int64_t num_chunks = ceil_div(Nt, kc);
-    const int64_t items = num_chunks * sched.tiles;
-    TQ_CHECK_ARG(items < (1ll << 31), "tq_hessian_accum: too many work items");
+    sched.num_chunks = (int)num_chunks;
+    const int64_t items = num_chunks * tiles;
 
     const uint32_t fmt = (dtype == TQ_F16) ? 0u : 1u;
     // tcgen05 instruction descriptor (kind::f16): D=f32, A/B format, A and B MN-major, N=256, M=128
@@ -268,7 +307,7 @@ int hessian_accum_tcgen05(float* H, int64_t ldh, const void* X, int64_t Nt, int6
         attr_set = true;
     }
     const int grid = (int)((items < sms) ? items : sms);
-    hessian_tc_kernel<<<grid, HT_THREADS, HT_SMEM, st>>>(map_x, map_h, (int)Nt, (int)kc, (int)num_chunks, sched, idesc);
+    hessian_tc_kernel<<<grid, HT_THREADS, HT_SMEM, st>>>(map_x, map_h, (int)Nt, (int)kc, sched, idesc);
     TQ_LAUNCH_CHECK("hessian_tc_kernel");
     return 0;
 }
