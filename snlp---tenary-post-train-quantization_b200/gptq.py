@@ -45,6 +45,7 @@ class HessianState:
         self.hessian_path = _lib.HESS_AUTO
         self._upper_only = False      # the tcgen05 path fills only tiles touching the upper triangle
         self._cache = {}
+        self._cache_events = {}
 
     def add_batch(self, inp: torch.Tensor):
         lib = _lib.load()
@@ -97,6 +98,10 @@ class HessianState:
         Hinv = cholesky_inverse(cholesky(Hd)); ``info`` is a device int (0 = ok)."""
         key = float(percdamp)
         if key in self._cache:
+            # linears sharing this Hessian may sweep on other streams than the one the inverse was enqueued on
+            ev = self._cache_events.get(key)
+            if ev is not None and ev[1] != torch.cuda.current_stream(self.device):
+                torch.cuda.current_stream(self.device).wait_event(ev[0])
             return self._cache[key]
         if self.nsamples <= 0:
             raise RuntimeError("quantize() called before add_batch(): the Hessian is empty")
@@ -117,6 +122,9 @@ class HessianState:
         for t in (work, scratch):
             t.record_stream(torch.cuda.current_stream(dev))
         self._cache[key] = (Hd, Hinv, info)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        self._cache_events[key] = (ev, torch.cuda.current_stream(dev))
         return self._cache[key]
 
 
@@ -238,6 +246,9 @@ class GPTQ:
             with torch.cuda.stream(stream):
                 Hinv = torch.linalg.pinv(Hd)          # library SVD, as in the reference
                 self.state._cache[float(self.percdamp)] = (Hd, Hinv, torch.zeros_like(info))
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                self.state._cache_events[float(self.percdamp)] = (ev, stream)
                 alpha, mu, T8, perm = run(Hinv)
             stream.synchronize()
         self.alpha = alpha.to(self.dtype)

@@ -89,12 +89,14 @@ class LayerDriver:
 
 class HostPipeline:
     def __init__(self, device, block_size: int = 128, percdamp: float = 0.01, use_ssr: bool = True,
-                 aga: str = "hessian", share_inputs: bool = False):
+                 aga: str = "hessian", share_inputs: bool = False, num_streams: int = 3):
         self.device = torch.device(device)
         self.block_size, self.percdamp, self.use_ssr, self.aga = block_size, percdamp, use_ssr, aga
         self.share_inputs = share_inputs
         self.copy_stream = torch.cuda.Stream(self.device)
         self.out_stream = torch.cuda.Stream(self.device)
+        self.chain_streams = [torch.cuda.Stream(self.device) for _ in range(max(1, num_streams))]
+        self._free_events = [None, None]
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._slots = {}
@@ -110,41 +112,67 @@ class HostPipeline:
             self._slots[key] = buf
         return buf[:need].view(shape)
 
-    def run(self, groups: Sequence[Tuple[torch.Tensor, List[Tuple[str, torch.Tensor]]]]) -> List[Dict[str, torch.Tensor]]:
-        """groups: [(X_host (pinned, (Nt, m) or (B, L, m)), [(name, W_host (pinned fp32 (n, m))), ...]), ...]
-        -- each group is one calibration input and the linears that read it.  Returns, per linear in
-        order, {'name', 'alpha', 'mu', 'T' (int8), 'perm'} in pinned host memory."""
+    def _stage(self, gi: int, group):
+        """Enqueue the host->device copies of one group on the copy stream (slot gi & 1); returns the device views and
+        the event that marks them landed."""
+        x_host, lins = group
+        slot = gi & 1
+        with torch.cuda.stream(self.copy_stream):
+            if self._free_events[slot] is not None:
+                self.copy_stream.wait_event(self._free_events[slot])
+            x_dev = self._slot("x", slot, tuple(x_host.shape), x_host.dtype)
+            x_dev.copy_(x_host, non_blocking=True)
+            self.h2d_bytes += x_host.numel() * x_host.element_size()
+            w_devs = []
+            for li, (name, w_host) in enumerate(lins):
+                w_dev = self._slot(f"w{li}", slot, tuple(w_host.shape), w_host.dtype)
+                w_dev.copy_(w_host, non_blocking=True)
+                self.h2d_bytes += w_host.numel() * w_host.element_size()
+                w_devs.append(w_dev)
+            ready = torch.cuda.Event()
+            ready.record(self.copy_stream)
+        return x_dev, w_devs, ready
+
+    def run_iter(self, groups: Iterable[Tuple[torch.Tensor, List[Tuple[str, torch.Tensor]]]]):
+        """Generator form of run(): yields the result dicts of one group at a time (their device->host copies may still
+        be in flight on the output stream: call ``synchronize()`` or use run()).  The copies of group g+1 are enqueued
+        BEFORE the compute of group g is, so they overlap it even though finishing a linear blocks the host once (the
+        Cholesky status read, gptq.py:104-106); a model's layers can be streamed through one call."""
         compute = torch.cuda.current_stream(self.device)
-        results = []
-        free_events = [None, None]           # slot reusable once the compute stream is done with it
-        pending_out = []
-        for gi, (x_host, lins) in enumerate(groups):
-            slot = gi & 1
-            with torch.cuda.stream(self.copy_stream):
-                if free_events[slot] is not None:
-                    self.copy_stream.wait_event(free_events[slot])
-                x_dev = self._slot("x", slot, tuple(x_host.shape), x_host.dtype)
-                x_dev.copy_(x_host, non_blocking=True)
-                self.h2d_bytes += x_host.numel() * x_host.element_size()
-                w_devs = []
-                for li, (name, w_host) in enumerate(lins):
-                    w_dev = self._slot(f"w{li}", slot, tuple(w_host.shape), w_host.dtype)
-                    w_dev.copy_(w_host, non_blocking=True)
-                    self.h2d_bytes += w_host.numel() * w_host.element_size()
-                    w_devs.append(w_dev)
-                ready = torch.cuda.Event()
-                ready.record(self.copy_stream)
+        self._free_events = [None, None]     # slot reusable once the compute stream is done with it
+        it = iter(groups)
+        nxt = next(it, None)
+        staged = self._stage(0, nxt) if nxt is not None else None
+        gi = 0
+        while nxt is not None:
+            cur, (x_dev, w_devs, ready) = nxt, staged
+            nxt = next(it, None)
             compute.wait_event(ready)
+            x_host, lins = cur
             shared = HessianState(x_host.shape[-1], self.device) if self.share_inputs else None
-            if shared is not None:
-                shared.add_batch(x_dev)
+            gs = []
             for (name, _), w_dev in zip(lins, w_devs):
                 g = GPTQ(LinearView(w_dev), self.block_size, self.percdamp, hessian=shared)
-                if shared is None:
+                if shared is None or shared.nsamples == 0:
                     g.add_batch(x_dev)
-                alpha, mu, _, perm = g.quantize(use_ssr=self.use_ssr, aga=self.aga)
+                gs.append(g)
+            x_done = torch.cuda.Event()
+            x_done.record(compute)
+            # the chains of the group's linears are independent: spread them over the side streams
+            for li, g in enumerate(gs):
+                s = self.chain_streams[li % len(self.chain_streams)]
+                s.wait_event(x_done)
+                with torch.cuda.stream(s):
+                    g.enqueue(use_ssr=self.use_ssr, aga=self.aga)
+            # the other slot's previous occupant (group gi - 1) has been finished on the host: prefetch group gi + 1
+            # now, while this group's kernels run
+            if nxt is not None:
+                staged = self._stage(gi + 1, nxt)
+            out_group = []
+            for (name, _), g in zip(lins, gs):
+                alpha, mu, _, perm = g.finish()
                 done = torch.cuda.Event()
-                done.record(compute)
+                done.record(compute)       # finish() synchronised the chain's stream; its dtype conversions ran here
                 with torch.cuda.stream(self.out_stream):
                     self.out_stream.wait_event(done)
                     out = {"name": name}
@@ -154,10 +182,25 @@ class HostPipeline:
                         t.record_stream(self.out_stream)
                         self.d2h_bytes += t.numel() * t.element_size()
                         out[key] = h
-                results.append(out)
+                out_group.append(out)
+            for s in self.chain_streams:
+                compute.wait_stream(s)
             ev = torch.cuda.Event()
             ev.record(compute)
-            free_events[slot] = ev
+            self._free_events[gi & 1] = ev
+            gi += 1
+            yield out_group
+
+    def synchronize(self):
         self.out_stream.synchronize()
-        compute.synchronize()
+        torch.cuda.current_stream(self.device).synchronize()
+
+    def run(self, groups: Sequence[Tuple[torch.Tensor, List[Tuple[str, torch.Tensor]]]]) -> List[Dict[str, torch.Tensor]]:
+        """groups: [(X_host (pinned, (Nt, m) or (B, L, m)), [(name, W_host (pinned fp32 (n, m))), ...]), ...]
+        -- each group is one calibration input and the linears that read it.  Returns, per linear in
+        order, {'name', 'alpha', 'mu', 'T' (int8), 'perm'} in pinned host memory."""
+        results = []
+        for out_group in self.run_iter(groups):
+            results.extend(out_group)
+        self.synchronize()
         return results

@@ -186,6 +186,7 @@ class ShardedLayer:
                 dist.broadcast(Hinv, src=owner, group=ctx.group)
                 dist.broadcast(info, src=owner, group=ctx.group)
                 st._cache[float(self.percdamp)] = (Hd, Hinv, info)
+                st._cache_events.pop(float(self.percdamp), None)
             lo, hi = ctx.row_range(W.shape[0])
             g = GPTQ(LinearView(W[lo:hi]), self.block_size, self.percdamp, hessian=st)
             if ctx.world > 1:

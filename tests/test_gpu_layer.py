@@ -209,3 +209,42 @@ def test_layer_driver_streams_match_sequential():
                 assert g.info == 0
                 got = dict(alpha=g.alpha.cpu().numpy(), mu=g.mu.cpu().numpy(), T=g.T.cpu().numpy(), perm=g.perm.cpu().numpy())
                 parity.assert_layer_parity(got, ref[nm], what=f"{nm}/streams={streams}/rep={rep}")
+
+
+@pytest.mark.parametrize("share", [False, True])
+def test_host_pipeline_matches_device_api(share):
+    """HostPipeline (pinned host in, pinned host out, copies double-buffered against the kernels, the group's chains
+    on side streams) returns what the plain device API returns; with share_inputs the linears of a group use one
+    Hessian and one inverse.  Three passes over the groups, as three transformer layers would."""
+    import tq100
+    from tq100.pipeline import HostPipeline
+    groups_spec = [(640, [("q", 384), ("k", 256), ("v", 384)]), (384, [("o", 640)]), (520, [("gate", 300), ("up", 300)])]
+    groups, ref = [], {}
+    for gi, (m, lins) in enumerate(groups_spec):
+        X = synth.make_activations(4, 256, m, seed=400 + gi)
+        xh = torch.from_numpy(X).pin_memory()
+        entry = []
+        for li, (nm, n) in enumerate(lins):
+            W = synth.make_weight(n, m, seed=500 + 10 * gi + li)
+            entry.append((nm, torch.from_numpy(W).pin_memory()))
+            g = tq100.GPTQ(_layer(W))
+            g.add_batch(torch.from_numpy(X).to(DEV))
+            a, u, T, p = g.quantize(use_ssr=True)
+            ref[nm] = dict(alpha=a.cpu().numpy(), mu=u.cpu().numpy(), T=T.cpu().numpy(), perm=p.cpu().numpy())
+        groups.append((xh, entry))
+    pipe = HostPipeline(DEV, use_ssr=True, aga="hessian", share_inputs=share, num_streams=2)
+    seen = 0
+    for out_group in pipe.run_iter(groups * 3):
+        pipe.synchronize()
+        for out in out_group:
+            assert not out["T"].is_cuda and out["T"].dtype == torch.int8 and out["perm"].dtype == torch.int64
+            got = dict(alpha=out["alpha"].numpy(), mu=out["mu"].numpy(), T=out["T"].numpy().astype(np.float32),
+                       perm=out["perm"].numpy())
+            parity.assert_layer_parity(got, ref[out["name"]], what=f"host pipeline {out['name']} share={share}")
+            seen += 1
+    assert seen == 3 * 6
+    res = pipe.run(groups)
+    assert [r["name"] for r in res] == ["q", "k", "v", "o", "gate", "up"]
+    x_bytes = sum(x.numel() * 2 for x, _ in groups)
+    w_bytes = sum(w.numel() * 4 for _, e in groups for _, w in e)
+    assert pipe.h2d_bytes == 4 * (x_bytes + w_bytes)
