@@ -348,41 +348,25 @@ def main():
         host_acts = {k: v.cpu().pin_memory() for k, v in acts.items()}                    # already this rank's samples
         slabs = {name: ctx.row_range(n) for name, n, m, _ in lins}
         host_w = {name: weights[0][name][slabs[name][0]:slabs[name][1]].cpu().pin_memory() for name, _, _, _ in lins}
-        dev_acts = {k: torch.empty_like(v) for k, v in acts.items()}
-        dev_w = {name: torch.empty_like(weights[0][name]) for name, _, _, _ in lins}
-        h2d = d2h = 0
-
-        def one_layer():
-            nonlocal h2d, d2h
-            for k in host_acts:
-                dev_acts[k].copy_(host_acts[k], non_blocking=True)
-                h2d += host_acts[k].numel() * host_acts[k].element_size()
-            for name, (lo, hi) in slabs.items():
-                dev_w[name][lo:hi].copy_(host_w[name], non_blocking=True)
-                h2d += host_w[name].numel() * 4
-            out = sharded_layer.quantize([(name, dev_w[name], dev_acts[src]) for name, n, m, src in lins], use_ssr=True)
-            res = []
-            for name, alpha, mu, T8, perm, _ in out:
-                for t in (alpha, mu, T8, perm):
-                    hbuf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-                    hbuf.copy_(t, non_blocking=True)
-                    d2h += t.numel() * t.element_size()
-                    res.append(hbuf)
-            return res
-
-        one_layer()
+        one_layer = (host_acts, [(name, host_w[name], n, src) for name, n, m, src in lins])
+        spipe = par.ShardedHostPipeline(ctx, block_size=128, percdamp=0.01, use_ssr=True, aga="hessian")
+        for keep in spipe.run_iter([one_layer]):                   # warm-up (device slots, pinned outputs)
+            pass
+        spipe.synchronize()
         barrier()
-        h2d = d2h = 0
+        spipe.h2d_bytes = spipe.d2h_bytes = 0
         t0 = time.perf_counter()
-        for _ in range(cfg["layers"]):
-            keep = one_layer()
+        for keep in spipe.run_iter([one_layer] * cfg["layers"]):
+            pass
+        spipe.synchronize()
         barrier()
         dt = time.perf_counter() - t0
-        e2e = {"value": dt, "unit": "s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "note": "per rank: its calibration samples and its row slab of each weight copied from pinned host memory, "
+        e2e = {"value": dt, "unit": "s", "h2d_bytes_per_step": int(spipe.h2d_bytes), "d2h_bytes_per_step": int(spipe.d2h_bytes),
+               "note": "ShardedHostPipeline per rank: its calibration samples and its row slab of each weight copied from "
+                       "pinned host memory (next layer's copies enqueued before this layer's kernels), "
                        "ShardedLayer.quantize, its slabs of alpha/mu/T(int8) + perm copied back; bytes are per rank; "
                        "wall clock around all layers with barriers, max over ranks"}
-        del host_acts, host_w, dev_acts, dev_w, keep
+        del host_acts, host_w, spipe, keep
     if e2e is not None and world > 1:
         t = torch.tensor([e2e["value"]], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

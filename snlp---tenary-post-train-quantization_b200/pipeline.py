@@ -6,6 +6,7 @@ traffic of the next input overlaps Hessian + sweep of the current one.  This is 
 ``bench.py`` times as ``e2e``; the kernels are the same ones ``GPTQ`` launches.
 """
 
+import collections
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import torch
@@ -89,14 +90,15 @@ class LayerDriver:
 
 class HostPipeline:
     def __init__(self, device, block_size: int = 128, percdamp: float = 0.01, use_ssr: bool = True,
-                 aga: str = "hessian", share_inputs: bool = False, num_streams: int = 3):
+                 aga: str = "hessian", share_inputs: bool = False, num_streams: int = 3, depth: int = 3):
         self.device = torch.device(device)
         self.block_size, self.percdamp, self.use_ssr, self.aga = block_size, percdamp, use_ssr, aga
         self.share_inputs = share_inputs
         self.copy_stream = torch.cuda.Stream(self.device)
         self.out_stream = torch.cuda.Stream(self.device)
         self.chain_streams = [torch.cuda.Stream(self.device) for _ in range(max(1, num_streams))]
-        self._free_events = [None, None]
+        self.depth = max(1, int(depth))               # device-side input slots: depth - 1 groups are copied ahead
+        self._free_events = [None] * self.depth
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self._slots = {}
@@ -116,7 +118,7 @@ class HostPipeline:
         """Enqueue the host->device copies of one group on the copy stream (slot gi & 1); returns the device views and
         the event that marks them landed."""
         x_host, lins = group
-        slot = gi & 1
+        slot = gi % self.depth
         with torch.cuda.stream(self.copy_stream):
             if self._free_events[slot] is not None:
                 self.copy_stream.wait_event(self._free_events[slot])
@@ -139,14 +141,31 @@ class HostPipeline:
         BEFORE the compute of group g is, so they overlap it even though finishing a linear blocks the host once (the
         Cholesky status read, gptq.py:104-106); a model's layers can be streamed through one call."""
         compute = torch.cuda.current_stream(self.device)
-        self._free_events = [None, None]     # slot reusable once the compute stream is done with it
+        self._free_events = [None] * self.depth      # slot reusable once the compute stream is done with it
         it = iter(groups)
-        nxt = next(it, None)
-        staged = self._stage(0, nxt) if nxt is not None else None
+        staged = collections.deque()                 # (group, device views) of groups gi, gi+1, .. already enqueued
+        n_staged = 0
+
+        def top_up():
+            # keep depth - 1 groups in flight ahead of the one being computed; the slot a new group lands in was last
+            # used by a group that has been finished on the host
+            nonlocal n_staged
+            while len(staged) < self.depth - 1:
+                grp = next(it, None)
+                if grp is None:
+                    return
+                staged.append((grp, self._stage(n_staged, grp)))
+                n_staged += 1
+
+        top_up()
+        if not staged:
+            grp = next(it, None)
+            if grp is not None:                      # depth == 1: no prefetch
+                staged.append((grp, self._stage(n_staged, grp)))
+                n_staged += 1
         gi = 0
-        while nxt is not None:
-            cur, (x_dev, w_devs, ready) = nxt, staged
-            nxt = next(it, None)
+        while staged:
+            cur, (x_dev, w_devs, ready) = staged.popleft()
             compute.wait_event(ready)
             x_host, lins = cur
             shared = HessianState(x_host.shape[-1], self.device) if self.share_inputs else None
@@ -164,10 +183,8 @@ class HostPipeline:
                 s.wait_event(x_done)
                 with torch.cuda.stream(s):
                     g.enqueue(use_ssr=self.use_ssr, aga=self.aga)
-            # the other slot's previous occupant (group gi - 1) has been finished on the host: prefetch group gi + 1
-            # now, while this group's kernels run
-            if nxt is not None:
-                staged = self._stage(gi + 1, nxt)
+            # prefetch now, while this group's kernels run
+            top_up()
             out_group = []
             for (name, _), g in zip(lins, gs):
                 alpha, mu, _, perm = g.finish()
@@ -187,8 +204,15 @@ class HostPipeline:
                 compute.wait_stream(s)
             ev = torch.cuda.Event()
             ev.record(compute)
-            self._free_events[gi & 1] = ev
+            self._free_events[gi % self.depth] = ev
             gi += 1
+            if not staged:
+                top_up()
+                if not staged:
+                    grp = next(it, None)
+                    if grp is not None:
+                        staged.append((grp, self._stage(n_staged, grp)))
+                        n_staged += 1
             yield out_group
 
     def synchronize(self):

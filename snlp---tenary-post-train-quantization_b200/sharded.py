@@ -194,3 +194,114 @@ class ShardedLayer:
             alpha, mu, _, perm = g.quantize(use_ssr=use_ssr, aga=aga, max_iter=max_iter)
             out[i] = (name, alpha, mu, g.T_int8, perm, (lo, hi))
         return out
+
+
+class ShardedHostPipeline:
+    """ShardedLayer fed from pinned HOST memory, one rank's view: per transformer layer this rank's calibration
+    samples and its row slab of every weight are copied host->device on a side stream, the layer is quantized
+    (ShardedLayer.quantize), and the rank's slabs of alpha / mu / T (int8) plus perm go back to pinned host memory on
+    a second side stream.  The copies of layer l+1 are enqueued before the kernels of layer l, so they overlap."""
+
+    def __init__(self, ctx: ShardContext, block_size: int = 128, percdamp: float = 0.01, use_ssr: bool = True,
+                 aga: str = "hessian", depth: int = 2):
+        self.ctx = ctx
+        self.layer = ShardedLayer(ctx, block_size, percdamp)
+        self.use_ssr, self.aga = use_ssr, aga
+        self.depth = max(1, int(depth))
+        self.copy_stream = torch.cuda.Stream(ctx.device)
+        self.out_stream = torch.cuda.Stream(ctx.device)
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
+        self._bufs = {}
+        self._free_events = [None] * self.depth
+
+    def _buf(self, key, shape, dtype):
+        need = 1
+        for s in shape:
+            need *= s
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < need or buf.dtype != dtype:
+            buf = torch.empty(need, dtype=dtype, device=self.ctx.device)
+            self._bufs[key] = buf
+        return buf[:need].view(shape)
+
+    def _stage(self, li, layer):
+        inputs, lins = layer
+        slot = li % self.depth
+        with torch.cuda.stream(self.copy_stream):
+            if self._free_events[slot] is not None:
+                self.copy_stream.wait_event(self._free_events[slot])
+            x_dev = {}
+            for key, xh in inputs.items():
+                xd = self._buf(("x", key, slot), tuple(xh.shape), xh.dtype)
+                xd.copy_(xh, non_blocking=True)
+                self.h2d_bytes += xh.numel() * xh.element_size()
+                x_dev[key] = xd
+            w_dev = []
+            for i, (name, w_slab, n, key) in enumerate(lins):
+                lo, hi = self.ctx.row_range(n)
+                if w_slab.shape[0] != hi - lo:
+                    raise ValueError(f"{name}: expected this rank's row slab [{lo}, {hi}) of the weight")
+                wd = self._buf(("w", i, slot), (n, w_slab.shape[1]), w_slab.dtype)   # only the slab's rows are read
+                wd[lo:hi].copy_(w_slab, non_blocking=True)
+                self.h2d_bytes += w_slab.numel() * w_slab.element_size()
+                w_dev.append(wd)
+            ready = torch.cuda.Event()
+            ready.record(self.copy_stream)
+        return x_dev, w_dev, ready
+
+    def run_iter(self, layers):
+        """layers: iterable of (inputs, linears); inputs = {key: X_host (this rank's samples, pinned, (.., m))},
+        linears = [(name, W_host_slab (pinned fp32, this rank's rows), n (rows of the whole weight), key)].
+        Yields, per layer, [{'name', 'alpha', 'mu', 'T' (int8), 'perm', 'rows': (lo, hi)}] in pinned host memory (the
+        device->host copies may still be in flight: synchronize())."""
+        compute = torch.cuda.current_stream(self.ctx.device)
+        self._free_events = [None] * self.depth
+        it = iter(layers)
+        staged = []
+        n_staged = 0
+
+        def top_up(target):
+            nonlocal n_staged
+            while len(staged) < target:
+                lay = next(it, None)
+                if lay is None:
+                    return
+                staged.append((lay, self._stage(n_staged, lay)))
+                n_staged += 1
+
+        top_up(max(1, self.depth - 1))
+        li = 0
+        while staged:
+            (inputs, lins), (x_dev, w_dev, ready) = staged.pop(0)
+            compute.wait_event(ready)
+            # ShardedLayer.quantize blocks the host (Cholesky status reads): stage the next layer's copies first.
+            # With depth slots, depth - 1 layers are ahead; the slot a new layer lands in was freed on the host.
+            top_up(self.depth - 1)
+            out = self.layer.quantize([(name, wd, x_dev[key]) for (name, _, _, key), wd in zip(lins, w_dev)],
+                                      use_ssr=self.use_ssr, aga=self.aga)
+            done = torch.cuda.Event()
+            done.record(compute)
+            res = []
+            with torch.cuda.stream(self.out_stream):
+                self.out_stream.wait_event(done)
+                for name, alpha, mu, T8, perm, rows in out:
+                    d = {"name": name, "rows": rows}
+                    for k, t in (("alpha", alpha), ("mu", mu), ("T", T8), ("perm", perm)):
+                        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                        h.copy_(t, non_blocking=True)
+                        t.record_stream(self.out_stream)
+                        self.d2h_bytes += t.numel() * t.element_size()
+                        d[k] = h
+                    res.append(d)
+            ev = torch.cuda.Event()
+            ev.record(compute)
+            self._free_events[li % self.depth] = ev
+            li += 1
+            if not staged:
+                top_up(1)
+            yield res
+
+    def synchronize(self):
+        self.out_stream.synchronize()
+        torch.cuda.current_stream(self.ctx.device).synchronize()

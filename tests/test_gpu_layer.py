@@ -211,8 +211,8 @@ def test_layer_driver_streams_match_sequential():
                 parity.assert_layer_parity(got, ref[nm], what=f"{nm}/streams={streams}/rep={rep}")
 
 
-@pytest.mark.parametrize("share", [False, True])
-def test_host_pipeline_matches_device_api(share):
+@pytest.mark.parametrize("share,depth", [(False, 3), (True, 2), (False, 1)])
+def test_host_pipeline_matches_device_api(share, depth):
     """HostPipeline (pinned host in, pinned host out, copies double-buffered against the kernels, the group's chains
     on side streams) returns what the plain device API returns; with share_inputs the linears of a group use one
     Hessian and one inverse.  Three passes over the groups, as three transformer layers would."""
@@ -232,7 +232,7 @@ def test_host_pipeline_matches_device_api(share):
             a, u, T, p = g.quantize(use_ssr=True)
             ref[nm] = dict(alpha=a.cpu().numpy(), mu=u.cpu().numpy(), T=T.cpu().numpy(), perm=p.cpu().numpy())
         groups.append((xh, entry))
-    pipe = HostPipeline(DEV, use_ssr=True, aga="hessian", share_inputs=share, num_streams=2)
+    pipe = HostPipeline(DEV, use_ssr=True, aga="hessian", share_inputs=share, num_streams=2, depth=depth)
     seen = 0
     for out_group in pipe.run_iter(groups * 3):
         pipe.synchronize()
