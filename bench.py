@@ -185,6 +185,7 @@ def main():
     ap.add_argument("--streams", type=int, default=4, help="CUDA streams the per-linear prologue+sweep chains are spread over")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-shared", action="store_true", help="skip the secondary shared-Hessian (N1) measurement")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
@@ -312,6 +313,31 @@ def main():
                 "flops_counted": "useful SYRK flops Nt*m*(m+1) per launch (dense-equivalent 2*Nt*m^2 is 2x)",
                 "share_of_step": h_ms / ms if ms > 0 else None, "launches": len(hess_events)}
 
+    # ---- SURVEY 8(f) N1, reported beside the headline: linears that read the same activations (q,k,v; gate,up) share one
+    # Hessian and one inverse -- 4 instead of 7 per layer, outputs unchanged.  The headline `value` above keeps the
+    # reference's 7 (main.py:289-299 computes one per linear).
+    n1 = None
+    if world == 1 and not args.no_shared:
+        shared_driver = LayerDriver(dev, block_size=128, percdamp=0.01, num_streams=args.streams, share_inputs=True)
+
+        def quantize_model_shared():
+            for li in range(cfg["layers"]):
+                results_keep["last"] = shared_driver.quantize(
+                    [(name, weights[li][name], acts[src]) for name, n, m, src in lins], use_ssr=True)
+
+        quantize_model_shared()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            quantize_model_shared()
+        s1.record()
+        torch.cuda.synchronize()
+        n1_ms = s0.elapsed_time(s1) / args.steps
+        n1 = {"value": n1_ms / 1e3, "unit": "s", "ms_per_step": n1_ms, "hessians_per_layer": 4,
+              "note": "same workload with LayerDriver(share_inputs=True): one Hessian + inverse per distinct calibration "
+                      "input (SURVEY 8f N1); identical outputs; not the headline"}
+
     # ---- e2e: same API from pinned host buffers, copies inside the timed region ------------------
     e2e = None
     if not args.no_e2e and world == 1:
@@ -379,6 +405,8 @@ def main():
                 "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e}
         if args.layers != LLAMA2_7B["layers"]:
             line["config"]["workload"] += f" [DEBUG: only {args.layers} of 32 layers]"
+        if n1 is not None:
+            line["n1_shared_inputs"] = n1
         line["dtype_note"] = "fp32 arithmetic; fp16 activations enter the tensor cores exactly, fp32 accumulate"
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_arm()

@@ -2,7 +2,7 @@
 # ncu evidence for the current kernels: launch list of one layer + full captures of the top kernels.
 set +e
 mkdir -p gpurun_out
-CMD="python bench.py --gpus 1 --steps 1 --warmup 0 --layers 1 --no-e2e --no-cpu-baseline --streams 1"
+CMD="python bench.py --gpus 1 --steps 1 --warmup 0 --layers 1 --no-e2e --no-cpu-baseline --no-shared --streams 1"
 timeout 300 $CMD > gpurun_out/plain_prof.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_prof.log; exit 1; }
 echo "=== launch list"
 timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 8000 --csv --log-file gpurun_out/launches_r01b.csv $CMD > gpurun_out/ncu_l.log 2>&1; echo "exit $?"

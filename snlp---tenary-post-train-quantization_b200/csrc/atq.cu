@@ -291,11 +291,23 @@ aga_vector_kernel(const float* __restrict__ Hsrc, int64_t ldh, const int32_t* __
     __shared__ float red[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     // (independent of the AGA vector) fold the coefficient kernel's per-CTA partials of C 1 in a fixed order
+    // (blockDim / b threads per column take interleaved partials, then one thread adds their sums in order: the serial
+    // chain is csum_parts / 8 loads long instead of csum_parts)
     if (csum != nullptr) {
-        for (int i = threadIdx.x; i < b; i += blockDim.x) {
+        __shared__ double fold[1024];
+        const int subs = max(1, (int)blockDim.x / b);
+        const int sub = threadIdx.x / b, i = threadIdx.x - sub * b;
+        if (sub < subs) {
             double s = 0.0;
-            for (int t = 0; t < csum_parts; ++t) s += (double)csum_part[(int64_t)t * b + i];
-            csum[i] = s;
+#pragma unroll 4
+            for (int t = sub; t < csum_parts; t += subs) s += (double)csum_part[(int64_t)t * b + i];
+            fold[sub * b + i] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x < b) {
+            double s = 0.0;
+            for (int q = 0; q < subs; ++q) s += fold[q * b + threadIdx.x];
+            csum[threadIdx.x] = s;
         }
     }
     if (mode == TQ_AGA_NONE) return;

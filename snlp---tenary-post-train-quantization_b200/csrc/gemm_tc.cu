@@ -479,7 +479,12 @@ static int launch_gemm_impl(int mode, float* C, int64_t ldc, int64_t M, int64_t 
         TQ_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GX_SMEM));
         attr_set = true;
     }
-    const int sms = sm_count();
+    // Persistent CTAs of this kernel fill an SM's shared memory.  The chains of other linears on other streams are made of
+    // short one-CTA kernels (diagonal-block factorisation, block selection, ...); a few SMs are left to them so they do
+    // not queue behind every GEMM (TQ_GX_SPARE_SMS, default 8).
+    static const int spare = []() { const char* e = getenv("TQ_GX_SPARE_SMS"); return e ? atoi(e) : 8; }();
+    int sms = sm_count() - spare;
+    if (sms < 1) sms = 1;
     const int grid = p.tiles < sms ? p.tiles : sms;
     gemm_tf32x3_kernel<<<grid, GX_THREADS, GX_SMEM, st>>>(ops->ah, ops->al, ops->bh, ops->bl, p);
     TQ_LAUNCH_CHECK("gemm_tf32x3_kernel");
