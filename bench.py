@@ -170,8 +170,12 @@ def workload_config(args, reference=False):
             "baseline_config": "configs[1]", "order": "ssr", "aga": "hessian", "block_size": 128,
             "activations": "fp16, one layer's 4 distinct inputs (12.2 GB) reused for all 32 layers",
             "cache": "inputs (12.2 GB activations + 25.9 GB weights) far exceed the 126 MB L2; no explicit flush",
-            "hessians_per_layer": 7, "streams": args.streams, "parallelism": "1 GPU" if args.gpus == 1 else f"{args.gpus} GPUs: "
-            "Hessian sample-sharded + NCCL allreduce, sweep row-sharded, H^-1 replicated"}
+            "hessians_per_layer": 7, "streams": args.streams, "parallelism": "1 GPU" if args.gpus == 1 else (
+                f"{args.gpus} GPUs: Hessian sample-sharded, NCCL reduce of each H onto the rank that owns the linear, "
+                "whole linears dealt to ranks (no collective inside the sweep)"
+                if getattr(args, "shard_mode", "linears") == "linears" else
+                f"{args.gpus} GPUs: Hessian sample-sharded + NCCL allreduce, H^-1 dealt + broadcast, sweep row-sharded "
+                "(SSR statistics all-reduced per block)")}
 
 
 # ------------------------------------------------------------------------------------ GPU arm
@@ -183,6 +187,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layers", type=int, default=LLAMA2_7B["layers"], help="(debug) fewer layers; the line says so")
     ap.add_argument("--streams", type=int, default=4, help="CUDA streams the per-linear prologue+sweep chains are spread over")
+    ap.add_argument("--shard-mode", default="linears", choices=["linears", "rows"],
+                    help="N > 1: deal whole linears to ranks (default) or row-shard every linear (SSR statistics all-reduced)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-shared", action="store_true", help="skip the secondary shared-Hessian (N1) measurement")
@@ -242,7 +248,7 @@ def main():
 
     if world > 1:
         par.init_comm(ctx)
-    sharded_layer = par.ShardedLayer(ctx, block_size=128, percdamp=0.01)
+    sharded_layer = par.ShardedLayer(ctx, block_size=128, percdamp=0.01, mode=args.shard_mode, num_streams=args.streams)
     from tq100.pipeline import LayerDriver
     driver = LayerDriver(dev, block_size=128, percdamp=0.01, num_streams=args.streams)
 
@@ -372,10 +378,16 @@ def main():
         # runs the sharded layer (all-reduce of H, dealt inverses, row-slab sweeps), and copies its slabs of
         # alpha / mu / T (int8) and perm back to pinned host memory.
         host_acts = {k: v.cpu().pin_memory() for k, v in acts.items()}                    # already this rank's samples
-        slabs = {name: ctx.row_range(n) for name, n, m, _ in lins}
-        host_w = {name: weights[0][name][slabs[name][0]:slabs[name][1]].cpu().pin_memory() for name, _, _, _ in lins}
+        if args.shard_mode == "rows":
+            slabs = {name: ctx.row_range(n) for name, n, m, _ in lins}
+        else:
+            own = sharded_layer.owners([(n, m) for _, n, m, _ in lins])
+            slabs = {name: ((0, n) if own[i] == rank else None) for i, (name, n, m, _) in enumerate(lins)}
+        host_w = {name: (weights[0][name][slabs[name][0]:slabs[name][1]].cpu().pin_memory() if slabs[name] else None)
+                  for name, _, _, _ in lins}
         one_layer = (host_acts, [(name, host_w[name], n, src) for name, n, m, src in lins])
-        spipe = par.ShardedHostPipeline(ctx, block_size=128, percdamp=0.01, use_ssr=True, aga="hessian")
+        spipe = par.ShardedHostPipeline(ctx, block_size=128, percdamp=0.01, use_ssr=True, aga="hessian",
+                                        mode=args.shard_mode)
         for keep in spipe.run_iter([one_layer]):                   # warm-up (device slots, pinned outputs)
             pass
         spipe.synchronize()
@@ -388,9 +400,9 @@ def main():
         barrier()
         dt = time.perf_counter() - t0
         e2e = {"value": dt, "unit": "s", "h2d_bytes_per_step": int(spipe.h2d_bytes), "d2h_bytes_per_step": int(spipe.d2h_bytes),
-               "note": "ShardedHostPipeline per rank: its calibration samples and its row slab of each weight copied from "
+               "note": "ShardedHostPipeline per rank: its calibration samples and its part of the weights (--shard-mode) copied from "
                        "pinned host memory (next layer's copies enqueued before this layer's kernels), "
-                       "ShardedLayer.quantize, its slabs of alpha/mu/T(int8) + perm copied back; bytes are per rank; "
+                       "ShardedLayer.quantize, its alpha/mu/T(int8)/perm copied back; bytes are those of rank 0; "
                        "wall clock around all layers with barriers, max over ranks"}
         del host_acts, host_w, spipe, keep
     if e2e is not None and world > 1:

@@ -61,31 +61,34 @@ class LayerDriver:
                 if self.share_inputs:
                     shared[id(X)] = g.state
             gs.append(g)
-        import os, time
-        dbg = os.environ.get("TQ_DRIVER_DEBUG")
-        if dbg:
-            torch.cuda.synchronize()
-            print(f"[driver] hessians done", flush=True)
-            t_enq = time.perf_counter()
+        return self.run_chains(gs, use_ssr=use_ssr, aga=aga, max_iter=max_iter)
+
+    def run_chains(self, gs, use_ssr: bool = True, aga: str = "hessian", max_iter: int = 100):
+        """Prologue + sweep of every GPTQ in ``gs`` (Hessians already accumulated on the current stream), longest
+        chain first, spread over the side streams; returns ``gs`` finished."""
+        main = torch.cuda.current_stream(self.device)
         ready = torch.cuda.Event()
         ready.record(main)
-        # longest chains first so the tail is short
-        order = sorted(range(len(gs)), key=lambda i: -(gs[i].columns ** 2 + gs[i].rows * gs[i].columns / 8))
+        order = sorted(range(len(gs)), key=lambda i: -chain_cost(gs[i].rows, gs[i].columns))
         for slot, i in enumerate(order):
             s = self.streams[slot % len(self.streams)]
             s.wait_event(ready)
             with torch.cuda.stream(s):
                 gs[i].enqueue(use_ssr=use_ssr, aga=aga, max_iter=max_iter)
-        if dbg:
-            print(f"[driver] enqueue of all linears took {1e3 * (time.perf_counter() - t_enq):.1f} ms host time", flush=True)
         for i in order:
-            t0 = time.perf_counter()
             gs[i].finish()
-            if dbg:
-                print(f"[driver] finish {linears[i][0]}: {1e3 * (time.perf_counter() - t0):.1f} ms info={gs[i].info}", flush=True)
         for s in self.streams:
             main.wait_stream(s)
         return gs
+
+
+def chain_cost(n: int, m: int, block: int = 128) -> float:
+    """Estimated duration (ms, one B200) of one linear's prologue + sweep chain for an n x m weight: the damped inverse
+    is latency-bound, ~0.24 us per 1000 entries of H; a sweep block costs ~62 us of dependent small kernels plus the
+    feedback read-modify-write of the remaining columns.  Fitted to profiles/r01_layer_sweep.json; used only to order
+    chains and to deal linears to ranks."""
+    blocks = (m + block - 1) // block
+    return 0.24e-6 * m * m + blocks * (0.062 + 4.3e-9 * n * m)
 
 
 class HostPipeline:

@@ -21,11 +21,11 @@ import torch.distributed as dist
 try:
     from . import _lib
     from .gptq import GPTQ, HessianState
-    from .pipeline import LinearView  # noqa: F401
+    from .pipeline import LayerDriver, LinearView, chain_cost  # noqa: F401
 except ImportError:
     import _lib
     from gptq import GPTQ, HessianState
-    from pipeline import LinearView  # noqa: F401
+    from pipeline import LayerDriver, LinearView, chain_cost  # noqa: F401
 
 
 class ShardContext:
@@ -114,23 +114,94 @@ class ShardedGPTQ:
         return outs[0], outs[1], outs[2], perm
 
 
+def _shape_of(w):
+    return tuple(w.shape) if torch.is_tensor(w) else tuple(w)
+
+
+def deal_linears(shapes, world: int) -> List[int]:
+    """Owner rank of every linear for the linear-parallel mode: longest chain first onto the least loaded rank
+    (deterministic, identical on every rank).  shapes: [(n, m)]."""
+    load = [0.0] * world
+    owner = [0] * len(shapes)
+    for i in sorted(range(len(shapes)), key=lambda i: (-chain_cost(*shapes[i]), i)):
+        r = min(range(world), key=lambda r: (load[r], r))
+        owner[i] = r
+        load[r] += chain_cost(*shapes[i])
+    return owner
+
+
 class ShardedLayer:
     """One transformer layer's linears over a ShardContext (the multi-GPU form of the per-layer loop of
-    main.py:289-299):
-      1. every rank accumulates each linear's H over ITS calibration samples (tcgen05 SYRK);
-      2. one NCCL all-reduce per H (+ one for the token counts) -> identical H everywhere;
-      3. the damped Cholesky inverses are dealt round-robin to the ranks and broadcast (H^-1 is then
-         replicated, as the sweep needs it);
-      4. every rank sweeps its contiguous row slab of every linear; with SSR the per-block column
-         statistics are all-reduced inside the C driver loop (in-library NCCL communicator)."""
+    main.py:289-299).  Every rank accumulates each linear's H over ITS calibration samples (tcgen05 SYRK); then
 
-    def __init__(self, ctx: ShardContext, block_size: int = 128, percdamp: float = 0.01):
-        self.ctx, self.block_size, self.percdamp = ctx, block_size, percdamp
+    mode 'linears' (default): the linears are independent objects, so they are dealt to the ranks (deal_linears).
+      One NCCL reduce per H onto its owner; the owner runs the whole prologue + sweep chain of its linears on its
+      own streams -- no collective inside the sweep, no H^-1 exchange; results stay on the owner.
+    mode 'rows': one NCCL all-reduce per H; the damped inverses are dealt round-robin and broadcast; every rank
+      sweeps its contiguous row slab of every linear; with SSR the per-block column statistics are all-reduced
+      inside the C driver loop (in-library NCCL communicator).  Results are row slabs on every rank."""
+
+    def __init__(self, ctx: ShardContext, block_size: int = 128, percdamp: float = 0.01, mode: str = "linears",
+                 num_streams: int = 4):
+        if mode not in ("linears", "rows"):
+            raise ValueError("mode must be 'linears' or 'rows'")
+        self.ctx, self.block_size, self.percdamp, self.mode = ctx, block_size, percdamp, mode
+        self._driver = LayerDriver(ctx.device, block_size, percdamp, num_streams=num_streams) if mode == "linears" else None
+
+    def owners(self, shapes) -> List[int]:
+        """Owner rank per linear ((n, m) shapes in layer order) in mode 'linears'."""
+        return deal_linears(list(shapes), self.ctx.world)
+
+    def _quantize_by_linear(self, linears, use_ssr, aga, max_iter, hess_timing):
+        ctx = self.ctx
+        owner = self.owners([_shape_of(W) for _, W, _ in linears])
+        states = []
+        for (_, W, X) in linears:
+            st = HessianState(X.shape[-1], ctx.device)
+            if hess_timing is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            st.add_batch(X)
+            if hess_timing is not None:
+                e1.record()
+                hess_timing.append((e0, e1, X.numel() // X.shape[-1], X.shape[-1]))
+            states.append(st)
+        if ctx.world > 1:
+            counts = torch.tensor([st.nsamples for st in states], dtype=torch.int64, device=ctx.device)
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=ctx.group)
+            # widest first: the longest chain's Hessian lands on its owner first
+            for i in sorted(range(len(states)), key=lambda i: -states[i].columns):
+                dist.reduce(states[i].H, dst=owner[i], op=dist.ReduceOp.SUM, group=ctx.group)
+            for st, c in zip(states, counts.tolist()):
+                st.nsamples = int(c)
+                st._cache.clear()
+        mine = [i for i in range(len(linears)) if owner[i] == ctx.rank]
+        gs = []
+        for i in mine:
+            W = linears[i][1]
+            if not torch.is_tensor(W):
+                raise ValueError(f"{linears[i][0]}: this rank owns the linear and needs its weight, not just the shape")
+            gs.append(GPTQ(LinearView(W), self.block_size, self.percdamp, hessian=states[i]))
+        self._driver.run_chains(gs, use_ssr=use_ssr, aga=aga, max_iter=max_iter)
+        out = []
+        done = dict(zip(mine, gs))
+        for i, (name, W, _) in enumerate(linears):
+            g = done.get(i)
+            if g is None:
+                out.append((name, None, None, None, None, (0, 0)))
+            else:
+                out.append((name, g.alpha, g.mu, g.T_int8, g.perm, (0, g.rows)))
+        return out
 
     def quantize(self, linears, use_ssr: bool = True, aga: str = "hessian", max_iter: int = 100, hess_timing=None):
-        """linears: [(name, W (n, m) replicated on every rank, X_local (this rank's samples, (.., m)))].
-        Returns [(name, alpha_slab, mu_slab, T_int8_slab, perm, (row_lo, row_hi))] in the input order.
+        """linears: [(name, W (n, m), X_local (this rank's samples, (.., m)))].
+        mode 'linears': W is read only on the linear's owner (see owners()); other ranks may pass its (n, m) shape instead;
+          returns [(name, alpha, mu, T_int8, perm, (0, n))] with None tensors and rows (0, 0) for linears owned elsewhere.
+        mode 'rows': W replicated (only this rank's row slab is read); returns
+          [(name, alpha_slab, mu_slab, T_int8_slab, perm, (row_lo, row_hi))] in the input order.
         hess_timing: optional list that receives (start_event, end_event, tokens, m) per Hessian launch."""
+        if self.mode == "linears":
+            return self._quantize_by_linear(linears, use_ssr, aga, max_iter, hess_timing)
         ctx = self.ctx
         main = torch.cuda.current_stream(ctx.device)
         states = []
@@ -198,14 +269,15 @@ class ShardedLayer:
 
 class ShardedHostPipeline:
     """ShardedLayer fed from pinned HOST memory, one rank's view: per transformer layer this rank's calibration
-    samples and its row slab of every weight are copied host->device on a side stream, the layer is quantized
-    (ShardedLayer.quantize), and the rank's slabs of alpha / mu / T (int8) plus perm go back to pinned host memory on
-    a second side stream.  The copies of layer l+1 are enqueued before the kernels of layer l, so they overlap."""
+    samples and its part of the weights (mode 'linears': the whole weight of the linears it owns; mode 'rows': its
+    row slab of every weight) are copied host->device on a side stream, the layer is quantized
+    (ShardedLayer.quantize), and the rank's alpha / mu / T (int8) / perm go back to pinned host memory on a second
+    side stream.  The copies of layer l+1 are enqueued before the kernels of layer l, so they overlap."""
 
     def __init__(self, ctx: ShardContext, block_size: int = 128, percdamp: float = 0.01, use_ssr: bool = True,
-                 aga: str = "hessian", depth: int = 2):
+                 aga: str = "hessian", depth: int = 2, mode: str = "linears"):
         self.ctx = ctx
-        self.layer = ShardedLayer(ctx, block_size, percdamp)
+        self.layer = ShardedLayer(ctx, block_size, percdamp, mode=mode)
         self.use_ssr, self.aga = use_ssr, aga
         self.depth = max(1, int(depth))
         self.copy_stream = torch.cuda.Stream(ctx.device)
@@ -238,13 +310,22 @@ class ShardedHostPipeline:
                 self.h2d_bytes += xh.numel() * xh.element_size()
                 x_dev[key] = xd
             w_dev = []
-            for i, (name, w_slab, n, key) in enumerate(lins):
-                lo, hi = self.ctx.row_range(n)
-                if w_slab.shape[0] != hi - lo:
-                    raise ValueError(f"{name}: expected this rank's row slab [{lo}, {hi}) of the weight")
-                wd = self._buf(("w", i, slot), (n, w_slab.shape[1]), w_slab.dtype)   # only the slab's rows are read
-                wd[lo:hi].copy_(w_slab, non_blocking=True)
-                self.h2d_bytes += w_slab.numel() * w_slab.element_size()
+            by_linear = self.layer.mode == "linears"
+            owner = self.layer.owners([(n, inputs[key].shape[-1]) for _, _, n, key in lins]) if by_linear else None
+            for i, (name, w_host, n, key) in enumerate(lins):
+                m = inputs[key].shape[-1]
+                if by_linear:
+                    if owner[i] != self.ctx.rank:
+                        w_dev.append((n, m))                               # owned elsewhere: only the shape is needed
+                        continue
+                    lo, hi = 0, n
+                else:
+                    lo, hi = self.ctx.row_range(n)
+                if w_host is None or tuple(w_host.shape) != (hi - lo, m):
+                    raise ValueError(f"{name}: expected rows [{lo}, {hi}) of the weight on this rank")
+                wd = self._buf(("w", i, slot), (n, m), w_host.dtype)       # mode 'rows': only the slab's rows are read
+                wd[lo:hi].copy_(w_host, non_blocking=True)
+                self.h2d_bytes += w_host.numel() * w_host.element_size()
                 w_dev.append(wd)
             ready = torch.cuda.Event()
             ready.record(self.copy_stream)
@@ -252,9 +333,10 @@ class ShardedHostPipeline:
 
     def run_iter(self, layers):
         """layers: iterable of (inputs, linears); inputs = {key: X_host (this rank's samples, pinned, (.., m))},
-        linears = [(name, W_host_slab (pinned fp32, this rank's rows), n (rows of the whole weight), key)].
-        Yields, per layer, [{'name', 'alpha', 'mu', 'T' (int8), 'perm', 'rows': (lo, hi)}] in pinned host memory (the
-        device->host copies may still be in flight: synchronize())."""
+        linears = [(name, W_host (pinned fp32: this rank's rows -- the whole weight if it owns the linear, None if
+        another rank does, see ShardedLayer.owners; its row slab in mode 'rows'), n (rows of the whole weight), key)].
+        Yields, per layer, [{'name', 'rows': (lo, hi), and for rows held here 'alpha', 'mu', 'T' (int8), 'perm'}] in
+        pinned host memory (the device->host copies may still be in flight: synchronize())."""
         compute = torch.cuda.current_stream(self.ctx.device)
         self._free_events = [None] * self.depth
         it = iter(layers)
@@ -287,6 +369,9 @@ class ShardedHostPipeline:
                 self.out_stream.wait_event(done)
                 for name, alpha, mu, T8, perm, rows in out:
                     d = {"name": name, "rows": rows}
+                    if alpha is None:                                      # mode 'linears': owned by another rank
+                        res.append(d)
+                        continue
                     for k, t in (("alpha", alpha), ("mu", mu), ("T", T8), ("perm", perm)):
                         h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
                         h.copy_(t, non_blocking=True)

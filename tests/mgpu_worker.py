@@ -34,7 +34,43 @@ def main():
         full[name] = (W, X)
         Xl = torch.from_numpy(X[ctx.my_samples(samples)]).to(dev)
         lins.append((name, torch.from_numpy(W).to(dev), Xl))
-    layer = sharded.ShardedLayer(ctx)
+    def single_gpu(name, use_ssr):
+        W, X = full[name]
+        g = tq100.GPTQ(LinearView(torch.from_numpy(W).to(dev)))
+        g.add_batch(torch.from_numpy(X).to(dev))
+        a1, u1, T1, p1 = g.quantize(use_ssr=use_ssr)
+        return dict(alpha=a1.cpu().numpy(), mu=u1.cpu().numpy(), T=T1.cpu().numpy(), perm=p1.cpu().numpy())
+
+    def compare(name, use_ssr, got, tag):
+        ref = single_gpu(name, use_ssr)
+        same_perm = np.array_equal(got["perm"], ref["perm"])
+        agree = parity.code_agreement(got["T"], ref["T"])
+        print(f"[mgpu] {tag} {name} ssr={use_ssr}: perm equal={same_perm} code agreement={agree:.6f}", flush=True)
+        if not use_ssr or same_perm:
+            parity.assert_layer_parity(got, ref, what=f"{tag}/{name}/ssr={use_ssr}")
+        else:
+            assert set(got["perm"][:128].tolist()) == set(ref["perm"][:128].tolist())
+
+    # ---- mode 'linears': whole linears dealt to ranks, H reduced onto the owner, no collective in the sweep
+    by_linear = sharded.ShardedLayer(ctx, mode="linears", num_streams=2)
+    owner = by_linear.owners([(n, m) for _, n, m in shapes])
+    assert sorted(set(owner)) == list(range(min(world, len(shapes)))), owner
+    for use_ssr in (False, True):
+        # non-owners hand over the shape only
+        out = by_linear.quantize([(nm, W if owner[i] == rank else tuple(W.shape), X) for i, (nm, W, X) in enumerate(lins)],
+                                 use_ssr=use_ssr)
+        for i, (name, alpha, mu, T8, perm, rows) in enumerate(out):
+            if owner[i] != rank:
+                assert alpha is None and rows == (0, 0)
+                continue
+            assert rows == (0, full[name][0].shape[0])
+            got = dict(alpha=alpha.float().cpu().numpy(), mu=mu.float().cpu().numpy(), T=T8.cpu().numpy(),
+                       perm=perm.cpu().numpy())
+            compare(name, use_ssr, got, "linears")
+    dist.barrier()
+
+    # ---- mode 'rows': every linear row-sharded, SSR statistics all-reduced per block
+    layer = sharded.ShardedLayer(ctx, mode="rows")
     for use_ssr in (False, True):
         out = layer.quantize(lins, use_ssr=use_ssr)
         for (name, alpha, mu, T8, perm, (lo, hi)) in out:
@@ -55,41 +91,38 @@ def main():
             dist.all_gather(perms, perm)
             assert all(torch.equal(p, perms[0]) for p in perms), f"{name}: ranks chose different column orders"
             if rank == 0:
-                W, X = full[name]
-                g = tq100.GPTQ(LinearView(torch.from_numpy(W).to(dev)))
-                g.add_batch(torch.from_numpy(X).to(dev))
-                a1, u1, T1, p1 = g.quantize(use_ssr=use_ssr)
                 got = dict(alpha=A.cpu().numpy(), mu=U.cpu().numpy(), T=TT.cpu().numpy(), perm=perm.cpu().numpy())
-                ref = dict(alpha=a1.cpu().numpy(), mu=u1.cpu().numpy(), T=T1.cpu().numpy(), perm=p1.cpu().numpy())
-                same_perm = np.array_equal(got["perm"], ref["perm"])
-                agree = parity.code_agreement(got["T"], ref["T"])
-                print(f"[mgpu] {name} ssr={use_ssr}: perm equal={same_perm} code agreement={agree:.6f}", flush=True)
-                if not use_ssr or same_perm:
-                    parity.assert_layer_parity(got, ref, what=f"{name}/ssr={use_ssr}")
-                else:
-                    assert set(got["perm"][:128].tolist()) == set(ref["perm"][:128].tolist())
-    # host-resident form: pinned host slabs in, pinned host slabs out, two layers streamed through one call
-    direct = {name: (a.cpu(), u.cpu(), t.cpu(), p.cpu()) for name, a, u, t, p, _ in layer.quantize(lins, use_ssr=True)}
+                compare(name, use_ssr, got, "rows")
+    # host-resident form of both modes: pinned host in, pinned host out, two layers streamed through one call
     inputs = {name: lin[2].cpu().pin_memory() for (name, _, _), lin in zip(shapes, lins)}
-    hl = []
-    for (name, n, m), lin in zip(shapes, lins):
-        lo, hi = ctx.row_range(n)
-        hl.append((name, lin[1][lo:hi].cpu().pin_memory(), n, name))
-    pipe = sharded.ShardedHostPipeline(ctx, use_ssr=True)
-    seen = 0
-    for res in pipe.run_iter([(inputs, hl)] * 2):
-        pipe.synchronize()
-        for d in res:
-            a, u, t, p = direct[d["name"]]
-            assert not d["T"].is_cuda and d["rows"] == ctx.row_range(full[d["name"]][0].shape[0])
-            if torch.equal(d["perm"], p):
-                agree = (d["T"] == t).float().mean().item()
-                assert agree >= parity.CODE_AGREEMENT, (d["name"], agree)
-            else:      # the Hessian's reduce-add order is not fixed run to run: a tie at a top-k boundary may flip
-                assert set(d["perm"][:128].tolist()) == set(p[:128].tolist())
-            seen += 1
-    assert seen == 2 * len(shapes)
-    assert pipe.h2d_bytes == 2 * (sum(x.numel() * 2 for x in inputs.values()) + sum(w.numel() * 4 for _, w, _, _ in hl))
+    for mode, lay in (("rows", layer), ("linears", by_linear)):
+        direct = {name: (a, u, t, p) for name, a, u, t, p, _ in lay.quantize(lins, use_ssr=True)}
+        hl = []
+        for i, ((name, n, m), lin) in enumerate(zip(shapes, lins)):
+            if mode == "rows":
+                lo, hi = ctx.row_range(n)
+                hl.append((name, lin[1][lo:hi].cpu().pin_memory(), n, name))
+            else:
+                hl.append((name, lin[1].cpu().pin_memory() if owner[i] == rank else None, n, name))
+        pipe = sharded.ShardedHostPipeline(ctx, use_ssr=True, mode=mode)
+        seen = 0
+        for res in pipe.run_iter([(inputs, hl)] * 2):
+            pipe.synchronize()
+            for d in res:
+                a, u, t, p = direct[d["name"]]
+                if a is None:
+                    assert "T" not in d
+                    continue
+                assert not d["T"].is_cuda and d["T"].shape == t.shape
+                if torch.equal(d["perm"], p.cpu()):
+                    agree = (d["T"] == t.cpu()).float().mean().item()
+                    assert agree >= parity.CODE_AGREEMENT, (mode, d["name"], agree)
+                else:  # the Hessian's reduce-add order is not fixed run to run: a tie at a top-k boundary may flip
+                    assert set(d["perm"][:128].tolist()) == set(p[:128].tolist())
+                seen += 1
+        assert seen == 2 * (len(shapes) if mode == "rows" else sum(1 for o in owner if o == rank)), (mode, seen)
+        w_bytes = sum(w.numel() * 4 for _, w, _, _ in hl if w is not None)
+        assert pipe.h2d_bytes == 2 * (sum(x.numel() * 2 for x in inputs.values()) + w_bytes)
     dist.barrier()
     if rank == 0:
         print("MGPU_OK", flush=True)

@@ -37,6 +37,20 @@ def test_shard_context_partitions():
         assert max(sizes) - min(sizes) <= 4
 
 
+def test_deal_linears_balances_by_chain_cost():
+    from tq100.pipeline import chain_cost
+    from tq100.sharded import deal_linears
+    shapes = [(4096, 4096)] * 4 + [(11008, 4096)] * 2 + [(4096, 11008)]          # one LLaMA-2-7B layer
+    assert deal_linears(shapes, 1) == [0] * 7
+    for world in (2, 4, 8):
+        owner = deal_linears(shapes, world)
+        load = [sum(chain_cost(*s) for s, o in zip(shapes, owner) if o == r) for r in range(world)]
+        widest = chain_cost(4096, 11008)
+        assert owner[6] == 0                                   # the longest chain is dealt first
+        assert max(load) <= max(widest, sum(load) / world * 1.35)
+    assert len(set(deal_linears(shapes, 8))) == 7               # 7 linears on 7 of 8 ranks
+
+
 def _worker(rank, world, port, ret):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
@@ -99,6 +113,30 @@ def _worker(rank, world, port, ret):
         gathered = [torch.zeros(128, dtype=torch.int64) for _ in range(world)]
         dist.all_gather(gathered, torch.from_numpy(rem[order]))
         assert all(torch.equal(g, gathered[0]) for g in gathered)
+        # 4. linear-parallel mode: linears dealt to ranks, each H reduced onto its owner, the owner sweeps the whole
+        #    linear alone -> identical to the unsharded result, no collective in the sweep
+        from tq100.sharded import deal_linears
+        shapes = [(96, 384), (64, 256), (48, 256)]
+        owner = deal_linears(shapes, world)
+        assert owner == deal_linears(shapes, world) and set(owner) == set(range(world))
+        for li, (n2, m2) in enumerate(shapes):
+            W2 = synth.make_weight(n2, m2, seed=50 + li)
+            X2 = synth.make_activations(samples, seq, m2, seed=60 + li, lam=0.5).astype(np.float32)
+            H2, ns2 = np.zeros((m2, m2), dtype=np.float32), 0
+            for i in ctx.my_samples(samples):
+                H2, ns2 = oracle.hessian_add_batch(H2, ns2, X2[i])
+            H2t, ns2t = torch.from_numpy(H2), torch.tensor([ns2])
+            dist.reduce(H2t, dst=owner[li])
+            dist.all_reduce(ns2t)
+            if owner[li] == rank:
+                Hf, nf = np.zeros((m2, m2), dtype=np.float32), 0
+                for i in range(samples):
+                    Hf, nf = oracle.hessian_add_batch(Hf, nf, X2[i])
+                assert int(ns2t.item()) == nf
+                np.testing.assert_allclose(H2t.numpy(), Hf, rtol=1e-5, atol=1e-4)
+                got = oracle.quantize_layer(W2, H2t.numpy(), nf, 128, 0.01, "sequential")
+                ref = oracle.quantize_layer(W2, Hf, nf, 128, 0.01, "sequential")
+                assert (got[2] == ref[2]).mean() >= 0.999
         ret[rank] = "ok"
     finally:
         dist.destroy_process_group()
