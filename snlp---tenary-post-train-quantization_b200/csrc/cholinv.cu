@@ -360,15 +360,22 @@ static inline int64_t chol_split_floats(int64_t m) {
     return a > b ? a : b;
 }
 
-// a helper stream per caller stream: phase 2 (L^-1) chases phase 1 (potrf) panel by panel
-static cudaStream_t aux_stream_for(cudaStream_t st) {
-    static std::unordered_map<cudaStream_t, cudaStream_t> pool;
+// helper streams per caller stream: phase 2 (L^-1) chases phase 1 (potrf) panel by panel on `aux`; the bulk of every
+// trailing update runs on `bulk` (lowest priority) behind the look-ahead part
+struct ChainStreams {
+    cudaStream_t aux = nullptr, bulk = nullptr;
+};
+static ChainStreams helper_streams_for(cudaStream_t st) {
+    static std::unordered_map<cudaStream_t, ChainStreams> pool;
     auto it = pool.find(st);
     if (it != pool.end()) return it->second;
-    cudaStream_t aux = nullptr;
-    if (cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-    pool[st] = aux;
-    return aux;
+    ChainStreams cs;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);                 // lo = least priority (numerically greatest)
+    if (cudaStreamCreateWithFlags(&cs.aux, cudaStreamNonBlocking) != cudaSuccess) cs.aux = nullptr;
+    if (cudaStreamCreateWithPriority(&cs.bulk, cudaStreamNonBlocking, lo) != cudaSuccess) cs.bulk = nullptr;
+    pool[st] = cs;
+    return cs;
 }
 static cudaEvent_t chol_event(size_t i) {
     static std::vector<cudaEvent_t> pool;
@@ -417,8 +424,14 @@ extern "C" int tq_chol_inverse(float* Hinv, const float* Hd, int64_t m, float* w
         if (tc_potrf && (rc = gemm_operands_encode(&ops_potrf, Sh, Sl, CB, srows, Sh, Sl, CB, srows, CB))) return rc;
         if (tc_trtri && (rc = gemm_operands_encode(&ops_trtri, Sh, Sl, CB, srows, Bh, Bl, CB, mp, CB))) return rc;
     }
-    cudaStream_t aux = one_stream ? nullptr : aux_stream_for(st);
+    const ChainStreams helpers = one_stream ? ChainStreams() : helper_streams_for(st);
+    cudaStream_t aux = helpers.aux;
     cudaStream_t s2 = aux ? aux : st;                 // stream of phase 2
+    // look-ahead: of update k only the column panel k+1 (what the next diagonal block and trsm read) stays on `st`;
+    // the rest runs on `bulk` while `st` factors panel k+1 (TQ_CHOL_NO_LOOKAHEAD=1 keeps it all on `st`)
+    static const bool no_lookahead = []() { const char* e = getenv("TQ_CHOL_NO_LOOKAHEAD"); return e && atoi(e) != 0; }();
+    cudaStream_t bulk = (tc_potrf && !no_lookahead) ? helpers.bulk : nullptr;
+    bool bulk_pending = false;                        // an update on `bulk` has not been joined by `st` yet
 
     static bool attr_set = false;
     const int diag_smem = (2 * CB * CB_LD + 3 * SB * (SB + 1)) * (int)sizeof(float);
@@ -452,12 +465,30 @@ extern "C" int tq_chol_inverse(float* Hinv, const float* Hd, int64_t m, float* w
                     return rc;
         }
         if (aux) {
-            TQ_CUDA(cudaEventRecord(chol_event(k), st));
-            TQ_CUDA(cudaStreamWaitEvent(aux, chol_event(k), 0));
+            TQ_CUDA(cudaEventRecord(chol_event(3 * k), st));
+            TQ_CUDA(cudaStreamWaitEvent(aux, chol_event(3 * k), 0));
         }
         if (below > 0) {
-            if (tc_potrf) {
-                // A_ij -= L_ik L_jk' on the tensor cores: both operands are the freshly solved panel
+            if (tc_potrf && bulk) {
+                // A_ij -= L_ik L_jk' on the tensor cores: both operands are the freshly solved panel.
+                // (a) column panel k+1 on `st` -- it also receives the bulk of update k-1, so join that first
+                if (bulk_pending) TQ_CUDA(cudaStreamWaitEvent(st, chol_event(3 * (k - 1) + 2), 0));
+                const int64_t la = below < CB ? below : CB;
+                if ((rc = launch_gemm_tf32x3_rows(GX_SUB_LOWER, L + (int64_t)(k0 + CB) * ld + (k0 + CB), ld, below, la,
+                                                  &ops_potrf, off, off, nullptr, 0, st)))
+                    return rc;
+                bulk_pending = false;
+                // (b) the remaining columns on `bulk`, released only after (a) so the short look-ahead GEMM gets the SMs
+                if (below > CB) {
+                    TQ_CUDA(cudaEventRecord(chol_event(3 * k + 1), st));
+                    TQ_CUDA(cudaStreamWaitEvent(bulk, chol_event(3 * k + 1), 0));
+                    if ((rc = launch_gemm_tf32x3_rows(GX_SUB_LOWER, L + (int64_t)(k0 + 2 * CB) * ld + (k0 + 2 * CB), ld,
+                                                      below - CB, below - CB, &ops_potrf, off + CB, off + CB, nullptr, 0, bulk)))
+                        return rc;
+                    TQ_CUDA(cudaEventRecord(chol_event(3 * k + 2), bulk));
+                    bulk_pending = true;
+                }
+            } else if (tc_potrf) {
                 if ((rc = launch_gemm_tf32x3_rows(GX_SUB_LOWER, L + (int64_t)(k0 + CB) * ld + (k0 + CB), ld, below, below,
                                                   &ops_potrf, off, off, nullptr, 0, st)))
                     return rc;
@@ -486,9 +517,10 @@ extern "C" int tq_chol_inverse(float* Hinv, const float* Hd, int64_t m, float* w
             off += below;
         }
     }
+    // (every update on `bulk` has been joined by the look-ahead GEMM of the following panel)
     if (aux) {
-        TQ_CUDA(cudaEventRecord(chol_event(panels), aux));
-        TQ_CUDA(cudaStreamWaitEvent(st, chol_event(panels), 0));
+        TQ_CUDA(cudaEventRecord(chol_event(3 * panels), aux));
+        TQ_CUDA(cudaStreamWaitEvent(st, chol_event(3 * panels), 0));
     }
 
     // phase 3: Hinv = X'X (upper), then mirror
