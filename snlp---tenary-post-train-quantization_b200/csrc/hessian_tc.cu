@@ -16,6 +16,8 @@
 //               warps 4-7 epilogue (TMEM lane quarter = warp % 4)
 #include "tc_common.cuh"
 
+#include <stdlib.h>
+
 namespace tq {
 
 constexpr int HT_BM = 128, HT_BN = 256, HT_BK = 64, HT_STAGES = 4, HT_UMMA_K = 16;
@@ -285,7 +287,8 @@ int hessian_accum_tcgen05(float* H, int64_t ldh, const void* X, int64_t Nt, int6
     int64_t kc_l2 = (40ll << 20) / (2 * (m < 7168 ? m : 7168));
     kc_l2 = (kc_l2 / HT_BK) * HT_BK;
     if (kc_l2 < 256) kc_l2 = 256;
-    if (kc_l2 > 2048) kc_l2 = 2048;   // also bounds the length of one TMEM accumulation: the tensor core's fp32 add truncates, and
+    static const int kc_cap = []() { const char* e = getenv("TQ_HESS_KC_MAX"); return e ? atoi(e) : 2048; }();
+    if (kc_l2 > kc_cap) kc_l2 = kc_cap;   // also bounds the length of one TMEM accumulation: the tensor core's fp32 add truncates, and
                                       // a sum of squares over L tokens picks up a relative bias of ~L * 2^-25 (measured 2.8e-5 at
                                       // L = 4864, 9e-6 at 1792); 2048 is the reference's own per-add_batch granularity
     const int64_t want_chunks = ceil_div((int64_t)6 * sms, tiles_per_group);
