@@ -172,7 +172,8 @@ def workload_config(args, reference=False):
             "cache": "inputs (12.2 GB activations + 25.9 GB weights) far exceed the 126 MB L2; no explicit flush",
             "hessians_per_layer": 7, "streams": args.streams, "parallelism": "1 GPU" if args.gpus == 1 else (
                 f"{args.gpus} GPUs: Hessian sample-sharded, NCCL reduce of each H onto the rank that owns the linear, "
-                "whole linears dealt to ranks (no collective inside the sweep)"
+                "whole linears dealt to ranks (no collective inside their sweeps); a linear whose chain exceeds 1.5x a "
+                "rank's fair share (down_proj from 4 GPUs up) is split by rows after its owner broadcasts H^-1"
                 if getattr(args, "shard_mode", "linears") == "linears" else
                 f"{args.gpus} GPUs: Hessian sample-sharded + NCCL allreduce, H^-1 dealt + broadcast, sweep row-sharded "
                 "(SSR statistics all-reduced per block)")}
@@ -390,7 +391,8 @@ def main():
             slabs = {name: ctx.row_range(n) for name, n, m, _ in lins}
         else:
             own = sharded_layer.owners([(n, m) for _, n, m, _ in lins])
-            slabs = {name: ((0, n) if own[i] == rank else None) for i, (name, n, m, _) in enumerate(lins)}
+            slabs = {name: (ctx.row_range(n) if own[i] < 0 else (0, n) if own[i] == rank else None)
+                     for i, (name, n, m, _) in enumerate(lins)}
         host_w = {name: (weights[0][name][slabs[name][0]:slabs[name][1]].cpu().pin_memory() if slabs[name] else None)
                   for name, _, _, _ in lins}
         one_layer = (host_acts, [(name, host_w[name], n, src) for name, n, m, src in lins])

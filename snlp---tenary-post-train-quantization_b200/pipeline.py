@@ -66,6 +66,10 @@ class LayerDriver:
     def run_chains(self, gs, use_ssr: bool = True, aga: str = "hessian", max_iter: int = 100):
         """Prologue + sweep of every GPTQ in ``gs`` (Hessians already accumulated on the current stream), longest
         chain first, spread over the side streams; returns ``gs`` finished."""
+        return self.finish_chains(gs, self.enqueue_chains(gs, use_ssr=use_ssr, aga=aga, max_iter=max_iter))
+
+    def enqueue_chains(self, gs, use_ssr: bool = True, aga: str = "hessian", max_iter: int = 100):
+        """Asynchronous half of run_chains(): returns the order to hand to finish_chains()."""
         main = torch.cuda.current_stream(self.device)
         ready = torch.cuda.Event()
         ready.record(main)
@@ -75,6 +79,10 @@ class LayerDriver:
             s.wait_event(ready)
             with torch.cuda.stream(s):
                 gs[i].enqueue(use_ssr=use_ssr, aga=aga, max_iter=max_iter)
+        return order
+
+    def finish_chains(self, gs, order):
+        main = torch.cuda.current_stream(self.device)
         for i in order:
             gs[i].finish()
         for s in self.streams:

@@ -136,25 +136,40 @@ class ShardedLayer:
 
     mode 'linears' (default): the linears are independent objects, so they are dealt to the ranks (deal_linears).
       One NCCL reduce per H onto its owner; the owner runs the whole prologue + sweep chain of its linears on its
-      own streams -- no collective inside the sweep, no H^-1 exchange; results stay on the owner.
+      own streams -- no collective inside the sweep, no H^-1 exchange; results stay on the owner.  A linear whose
+      chain alone exceeds split_threshold x a rank's fair share (the 11008-wide down_proj from 4 GPUs up) is split:
+      its H is all-reduced, its owner inverts and broadcasts H^-1, and every rank sweeps its row slab of it.
     mode 'rows': one NCCL all-reduce per H; the damped inverses are dealt round-robin and broadcast; every rank
       sweeps its contiguous row slab of every linear; with SSR the per-block column statistics are all-reduced
       inside the C driver loop (in-library NCCL communicator).  Results are row slabs on every rank."""
 
     def __init__(self, ctx: ShardContext, block_size: int = 128, percdamp: float = 0.01, mode: str = "linears",
-                 num_streams: int = 4):
+                 num_streams: int = 4, split_threshold: Optional[float] = 1.5):
         if mode not in ("linears", "rows"):
             raise ValueError("mode must be 'linears' or 'rows'")
         self.ctx, self.block_size, self.percdamp, self.mode = ctx, block_size, percdamp, mode
+        self.split_threshold = split_threshold
         self._driver = LayerDriver(ctx.device, block_size, percdamp, num_streams=num_streams) if mode == "linears" else None
 
     def owners(self, shapes) -> List[int]:
-        """Owner rank per linear ((n, m) shapes in layer order) in mode 'linears'."""
-        return deal_linears(list(shapes), self.ctx.world)
+        """Mode 'linears': owner rank per linear ((n, m) shapes in layer order).  A linear whose chain is much longer
+        than a rank's fair share (chain_cost > split_threshold x total / world) is *split*: its owner (returned as
+        ``-1 - rank``, i.e. negative) computes the damped inverse and broadcasts it, then every rank sweeps its row slab
+        of that linear (as mode 'rows' does); W and the results of a split linear are row slabs on every rank."""
+        shapes = [tuple(s) for s in shapes]
+        owner = deal_linears(shapes, self.ctx.world)
+        if self.ctx.world > 1 and self.split_threshold is not None:
+            fair = sum(chain_cost(*s) for s in shapes) / self.ctx.world
+            owner = [(-1 - o) if chain_cost(*s) > self.split_threshold * fair else o for o, s in zip(owner, shapes)]
+        return owner
 
     def _quantize_by_linear(self, linears, use_ssr, aga, max_iter, hess_timing):
         ctx = self.ctx
+        main = torch.cuda.current_stream(ctx.device)
         owner = self.owners([_shape_of(W) for _, W, _ in linears])
+        split = [i for i, o in enumerate(owner) if o < 0]
+        if split and use_ssr and not _lib.comm_ready():
+            init_comm(ctx)                                   # row-sharded SSR all-reduces inside the C sweep loop
         states = []
         for (_, W, X) in linears:
             st = HessianState(X.shape[-1], ctx.device)
@@ -170,11 +185,34 @@ class ShardedLayer:
             counts = torch.tensor([st.nsamples for st in states], dtype=torch.int64, device=ctx.device)
             dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=ctx.group)
             # widest first: the longest chain's Hessian lands on its owner first
-            for i in sorted(range(len(states)), key=lambda i: -states[i].columns):
-                dist.reduce(states[i].H, dst=owner[i], op=dist.ReduceOp.SUM, group=ctx.group)
+            for i in sorted(range(len(states)), key=lambda i: (-states[i].columns, i)):
+                if owner[i] < 0:
+                    dist.all_reduce(states[i].H, op=dist.ReduceOp.SUM, group=ctx.group)
+                else:
+                    dist.reduce(states[i].H, dst=owner[i], op=dist.ReduceOp.SUM, group=ctx.group)
             for st, c in zip(states, counts.tolist()):
                 st.nsamples = int(c)
                 st._cache.clear()
+        # split linears first on their owner: the inverse is the longest single dependent chain of the layer
+        pending = {}
+        if split:
+            if not hasattr(self, "_inv_stream"):
+                self._inv_stream = torch.cuda.Stream(ctx.device)
+            self._inv_stream.wait_stream(main)
+            for i in split:
+                st, m = states[i], states[i].columns
+                if -1 - owner[i] == ctx.rank:
+                    with torch.cuda.stream(self._inv_stream):
+                        Hd, Hinv, info = st.damped_inverse(self.percdamp)
+                        done = torch.cuda.Event()
+                        done.record(self._inv_stream)
+                else:
+                    Hd = st.damped(self.percdamp)
+                    Hinv = torch.empty((m, m), dtype=torch.float32, device=ctx.device)
+                    info = torch.zeros(1, dtype=torch.int32, device=ctx.device)
+                    done = None
+                pending[i] = (Hd, Hinv, info, done)
+        # this rank's whole linears: chains on the side streams, asynchronous
         mine = [i for i in range(len(linears)) if owner[i] == ctx.rank]
         gs = []
         for i in mine:
@@ -182,21 +220,48 @@ class ShardedLayer:
             if not torch.is_tensor(W):
                 raise ValueError(f"{linears[i][0]}: this rank owns the linear and needs its weight, not just the shape")
             gs.append(GPTQ(LinearView(W), self.block_size, self.percdamp, hessian=states[i]))
-        self._driver.run_chains(gs, use_ssr=use_ssr, aga=aga, max_iter=max_iter)
+        order = self._driver.enqueue_chains(gs, use_ssr=use_ssr, aga=aga, max_iter=max_iter)
+        # split linears: inverse broadcast, then every rank sweeps its row slab (statistics all-reduced per block)
+        slabs = {}
+        for i in split:
+            name, W, _ = linears[i]
+            if not torch.is_tensor(W):
+                raise ValueError(f"{name}: a split linear needs (this rank's row slab of) its weight on every rank")
+            st = states[i]
+            Hd, Hinv, info, done = pending[i]
+            if done is not None:
+                main.wait_event(done)
+                for t in (Hd, Hinv, info):
+                    t.record_stream(main)
+            src = -1 - owner[i]
+            dist.broadcast(Hinv, src=src, group=ctx.group)
+            dist.broadcast(info, src=src, group=ctx.group)
+            st._cache[float(self.percdamp)] = (Hd, Hinv, info)
+            st._cache_events.pop(float(self.percdamp), None)
+            lo, hi = ctx.row_range(W.shape[0])
+            g = GPTQ(LinearView(W[lo:hi]), self.block_size, self.percdamp, hessian=st)
+            g.sweep_flags = _lib.SWEEP_ROW_SHARD
+            g.quantize(use_ssr=use_ssr, aga=aga, max_iter=max_iter)
+            slabs[i] = (g, (lo, hi))
+        self._driver.finish_chains(gs, order)
         out = []
-        done = dict(zip(mine, gs))
+        done_whole = dict(zip(mine, gs))
         for i, (name, W, _) in enumerate(linears):
-            g = done.get(i)
-            if g is None:
-                out.append((name, None, None, None, None, (0, 0)))
-            else:
+            if i in slabs:
+                g, rows = slabs[i]
+                out.append((name, g.alpha, g.mu, g.T_int8, g.perm, rows))
+            elif i in done_whole:
+                g = done_whole[i]
                 out.append((name, g.alpha, g.mu, g.T_int8, g.perm, (0, g.rows)))
+            else:
+                out.append((name, None, None, None, None, (0, 0)))
         return out
 
     def quantize(self, linears, use_ssr: bool = True, aga: str = "hessian", max_iter: int = 100, hess_timing=None):
         """linears: [(name, W (n, m), X_local (this rank's samples, (.., m)))].
         mode 'linears': W is read only on the linear's owner (see owners()); other ranks may pass its (n, m) shape instead;
-          returns [(name, alpha, mu, T_int8, perm, (0, n))] with None tensors and rows (0, 0) for linears owned elsewhere.
+          returns [(name, alpha, mu, T_int8, perm, (0, n))] with None tensors and rows (0, 0) for linears owned elsewhere;
+          a *split* linear (owners() < 0) needs W on every rank (only this rank's row slab is read) and returns row slabs.
         mode 'rows': W replicated (only this rank's row slab is read); returns
           [(name, alpha_slab, mu_slab, T_int8_slab, perm, (row_lo, row_hi))] in the input order.
         hess_timing: optional list that receives (start_event, end_event, tokens, m) per Hessian launch."""
@@ -314,12 +379,12 @@ class ShardedHostPipeline:
             owner = self.layer.owners([(n, inputs[key].shape[-1]) for _, _, n, key in lins]) if by_linear else None
             for i, (name, w_host, n, key) in enumerate(lins):
                 m = inputs[key].shape[-1]
-                if by_linear:
+                if by_linear and owner[i] >= 0:
                     if owner[i] != self.ctx.rank:
                         w_dev.append((n, m))                               # owned elsewhere: only the shape is needed
                         continue
                     lo, hi = 0, n
-                else:
+                else:                                                      # mode 'rows', or a split linear
                     lo, hi = self.ctx.row_range(n)
                 if w_host is None or tuple(w_host.shape) != (hi - lo, m):
                     raise ValueError(f"{name}: expected rows [{lo}, {hi}) of the weight on this rank")
@@ -334,7 +399,8 @@ class ShardedHostPipeline:
     def run_iter(self, layers):
         """layers: iterable of (inputs, linears); inputs = {key: X_host (this rank's samples, pinned, (.., m))},
         linears = [(name, W_host (pinned fp32: this rank's rows -- the whole weight if it owns the linear, None if
-        another rank does, see ShardedLayer.owners; its row slab in mode 'rows'), n (rows of the whole weight), key)].
+        another rank does, its row slab if the linear is split, see ShardedLayer.owners; its row slab in mode 'rows'),
+        n (rows of the whole weight), key)].
         Yields, per layer, [{'name', 'rows': (lo, hi), and for rows held here 'alpha', 'mu', 'T' (int8), 'perm'}] in
         pinned host memory (the device->host copies may still be in flight: synchronize())."""
         compute = torch.cuda.current_stream(self.ctx.device)

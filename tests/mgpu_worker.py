@@ -69,6 +69,38 @@ def main():
             compare(name, use_ssr, got, "linears")
     dist.barrier()
 
+    # ---- mode 'linears' with the longest linear split by rows (threshold lowered to force it at any world size)
+    hybrid = sharded.ShardedLayer(ctx, mode="linears", num_streams=2, split_threshold=0.3 * world)
+    h_owner = hybrid.owners([(n, m) for _, n, m in shapes])
+    assert any(o < 0 for o in h_owner) and any(o >= 0 for o in h_owner), h_owner
+    for use_ssr in (False, True):
+        out = hybrid.quantize([(nm, W if (h_owner[i] < 0 or h_owner[i] == rank) else tuple(W.shape), X)
+                               for i, (nm, W, X) in enumerate(lins)], use_ssr=use_ssr)
+        for i, (name, alpha, mu, T8, perm, rows) in enumerate(out):
+            n = full[name][0].shape[0]
+            if h_owner[i] >= 0:
+                if h_owner[i] == rank:
+                    got = dict(alpha=alpha.float().cpu().numpy(), mu=mu.float().cpu().numpy(), T=T8.cpu().numpy(),
+                               perm=perm.cpu().numpy())
+                    compare(name, use_ssr, got, "hybrid/whole")
+                continue
+            assert rows == ctx.row_range(n)
+            all_rows = [sharded.ShardContext(r, world).row_range(n) for r in range(world)]
+            mx = max(b - a for a, b in all_rows)
+
+            def gather_slab(t):
+                pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+                pad[: t.shape[0]] = t
+                parts = [torch.empty_like(pad) for _ in range(world)]
+                dist.all_gather(parts, pad)
+                return torch.cat([p[: b - a] for p, (a, b) in zip(parts, all_rows)], 0)
+
+            A, U, TT = gather_slab(alpha.float().contiguous()), gather_slab(mu.float().contiguous()), gather_slab(T8)
+            if rank == 0:
+                compare(name, use_ssr, dict(alpha=A.cpu().numpy(), mu=U.cpu().numpy(), T=TT.cpu().numpy(),
+                                            perm=perm.cpu().numpy()), "hybrid/split")
+    dist.barrier()
+
     # ---- mode 'rows': every linear row-sharded, SSR statistics all-reduced per block
     layer = sharded.ShardedLayer(ctx, mode="rows")
     for use_ssr in (False, True):
@@ -95,16 +127,18 @@ def main():
                 compare(name, use_ssr, got, "rows")
     # host-resident form of both modes: pinned host in, pinned host out, two layers streamed through one call
     inputs = {name: lin[2].cpu().pin_memory() for (name, _, _), lin in zip(shapes, lins)}
-    for mode, lay in (("rows", layer), ("linears", by_linear)):
+    for mode, lay, own in (("rows", layer, None), ("linears", by_linear, owner), ("hybrid", hybrid, h_owner)):
         direct = {name: (a, u, t, p) for name, a, u, t, p, _ in lay.quantize(lins, use_ssr=True)}
         hl = []
         for i, ((name, n, m), lin) in enumerate(zip(shapes, lins)):
-            if mode == "rows":
+            if mode == "rows" or own[i] < 0:
                 lo, hi = ctx.row_range(n)
                 hl.append((name, lin[1][lo:hi].cpu().pin_memory(), n, name))
             else:
-                hl.append((name, lin[1].cpu().pin_memory() if owner[i] == rank else None, n, name))
-        pipe = sharded.ShardedHostPipeline(ctx, use_ssr=True, mode=mode)
+                hl.append((name, lin[1].cpu().pin_memory() if own[i] == rank else None, n, name))
+        pipe = sharded.ShardedHostPipeline(ctx, use_ssr=True, mode="rows" if mode == "rows" else "linears")
+        if mode == "hybrid":
+            pipe.layer.split_threshold = hybrid.split_threshold
         seen = 0
         for res in pipe.run_iter([(inputs, hl)] * 2):
             pipe.synchronize()
@@ -120,7 +154,7 @@ def main():
                 else:  # the Hessian's reduce-add order is not fixed run to run: a tie at a top-k boundary may flip
                     assert set(d["perm"][:128].tolist()) == set(p[:128].tolist())
                 seen += 1
-        assert seen == 2 * (len(shapes) if mode == "rows" else sum(1 for o in owner if o == rank)), (mode, seen)
+        assert seen == 2 * (len(shapes) if mode == "rows" else sum(1 for o in own if o == rank or o < 0)), (mode, seen)
         w_bytes = sum(w.numel() * 4 for _, w, _, _ in hl if w is not None)
         assert pipe.h2d_bytes == 2 * (sum(x.numel() * 2 for x in inputs.values()) + w_bytes)
     dist.barrier()
