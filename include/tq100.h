@@ -67,6 +67,10 @@ long long   tq_launch_count(void);
  * X   [Nt, ldx] of `dtype`, row = token.  */
 int tq_hessian_accum(float* H, int64_t ldh, const void* X, int64_t Nt, int64_t m, int64_t ldx,
                      int dtype, int path, void* stream);
+/* development aid: device buffer (>= 32 long long) that receives clock64 stamps of the first panel's phases inside
+ * the diagonal-block kernel of tq_chol_inverse (scripts/diag_prof.py); NULL switches it off */
+void tq_debug_set_diag_prof(long long* dev_buf);
+
 /* lower triangle := upper triangle */
 int tq_symmetrize(float* H, int64_t ldh, int64_t m, void* stream);
 
