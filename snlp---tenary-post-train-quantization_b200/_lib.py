@@ -30,6 +30,7 @@ _SIGNATURES = {
     "tq_launch_count": (ctypes.c_longlong, []),
     "tq_hessian_accum": (_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _int, _int, _ptr]),
     "tq_symmetrize": (_int, [_ptr, _i64, _i64, _ptr]),
+    "tq_debug_set_diag_prof": (None, [_ptr]),
     "tq_hessian_finalize": (_int, [_ptr, _ptr, _i64, _dbl, _dbl, _ptr, _ptr]),
     "tq_chol_workspace_floats": (_i64, [_i64]),
     "tq_chol_inverse": (_int, [_ptr, _ptr, _i64, _ptr, _ptr, _ptr]),
