@@ -185,6 +185,32 @@ int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const float* Hd,
                    const int32_t* static_perm, int8_t* Torig, float* alpha, float* mu,
                    int32_t* perm, void* workspace, int64_t workspace_bytes, int flags, void* stream);
 
+/* ---- SURVEY 8f N2  TernaryLinear on 2-bit codes, model.py:17-127 -----------------------------------
+ * Layer format: codes u32 [n, wpr] (wpr >= tq_tl_words_per_row(m) = ceil(m/16)): word w of row r holds SWEEP
+ * positions 16w..16w+15, position p at bits 2(p%16)..+1, code = T[r, perm[p]] + 1 (utils.py:203 coding),
+ * positions >= m = code 1; so block k of alpha/mu (gptq.py:153-155) covers positions [k*block, (k+1)*block).
+ * wtab f32 [n, nb, 4] = (fl(mu-alpha), mu, fl(alpha+mu), 0): `alpha * T + mu` of model.py:108 evaluated and
+ * rounded in the layer dtype `wdtype` (TQ_F32/F16/BF16), indexed by code.  perm NULL = identity.
+ * block must be a multiple of 16 (else TQ_E_UNSUPPORTED).
+ *   tq_tl_pack     T int8 [n, m] in ORIGINAL positions (gptq.py:155) + perm -> codes
+ *   tq_tl_wtab     alpha, mu f32 [n, nb] -> wtab
+ *   tq_tl_gemv     y[t, r] = sum_p wtab[r, p/block][code(r,p)] * x[t, perm[p]] (+ bias[r]) for M tokens, i.e.
+ *                  model.py:75-95 with the dequantised weight of gptq.py:201-230; x [M, ldx] of xdtype, y f32
+ *                  [M, ldy]; meant for decode-sized M (4 tokens per launch)
+ *   tq_tl_dequant  dense Wq [n, ldw] of wdtype in ORIGINAL column positions (model.py:97-110 / gptq.py:201-230)
+ *   tq_tl_unpack   T int8 [n, m] in original positions */
+int64_t tq_tl_words_per_row(int64_t m);
+int tq_tl_pack(const int8_t* Torig, int64_t n, int64_t m, const int32_t* perm, uint32_t* codes, int64_t wpr,
+               void* stream);
+int tq_tl_wtab(const float* alpha, const float* mu, int64_t n, int64_t nb, int wdtype, float* wtab, void* stream);
+int tq_tl_gemv(const uint32_t* codes, int64_t wpr, const float* wtab, int64_t n, int64_t m, int64_t block,
+               const void* x, int xdtype, int64_t ldx, int64_t M, const int32_t* perm, const float* bias,
+               float* y, int64_t ldy, void* stream);
+int tq_tl_dequant(const uint32_t* codes, int64_t wpr, const float* wtab, int64_t n, int64_t m, int64_t block,
+                  const int32_t* perm, void* W, int wdtype, int64_t ldw, void* stream);
+int tq_tl_unpack(const uint32_t* codes, int64_t wpr, int64_t n, int64_t m, const int32_t* perm, int8_t* Torig,
+                 void* stream);
+
 /* ---- communicator for the row-sharded sweep ------------------------------------------
  * One process per GPU.  Rank 0 calls tq_comm_unique_id (128 bytes, host), ships the bytes to the other
  * ranks (torch.distributed broadcast), every rank calls tq_comm_init on its device.  NCCL is taken from

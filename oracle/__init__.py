@@ -47,3 +47,4 @@ from .gptq import (  # noqa: F401
     reconstruction_error,
 )
 from .pack import pack_ternary, unpack_ternary  # noqa: F401
+from . import ternary_linear  # noqa: F401  (model.py:17-127)

@@ -15,6 +15,24 @@ from .reorder import (  # noqa: F401
     apply_permutation_to_input,
 )
 from .gptq import GPTQ, GPTQQuantizer, HessianState, quantize_layer  # noqa: F401
-from .utils import pack_ternary, unpack_ternary  # noqa: F401
+from .utils import (  # noqa: F401
+    pack_ternary,
+    unpack_ternary,
+    compute_bits_per_weight,
+    stored_bits_per_weight,
+    save_quantized_model,
+    load_quantized_model,
+    set_seed,
+)
+from .model import (  # noqa: F401
+    TernaryLinear,
+    get_model_layers,
+    get_llm_layers,
+    find_linear_layers,
+    replace_linear_with_ternary,
+    get_model_type,
+    compute_model_size,
+    compute_compression_ratio,
+)
 
 __version__ = "0.1.0"

@@ -53,6 +53,12 @@ _SIGNATURES = {
     "tq_sweep_workspace_bytes": (_i64, [_i64, _i64, _i64]),
     "tq_sweep_layer": (_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _i64, _int, _int, _int, _ptr, _ptr,
                               _ptr, _ptr, _ptr, _ptr, _i64, _int, _ptr]),
+    "tq_tl_words_per_row": (_i64, [_i64]),
+    "tq_tl_pack": (_int, [_ptr, _i64, _i64, _ptr, _ptr, _i64, _ptr]),
+    "tq_tl_wtab": (_int, [_ptr, _ptr, _i64, _i64, _int, _ptr, _ptr]),
+    "tq_tl_gemv": (_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _int, _i64, _i64, _ptr, _ptr, _ptr, _i64, _ptr]),
+    "tq_tl_dequant": (_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _ptr, _int, _i64, _ptr]),
+    "tq_tl_unpack": (_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr]),
     "tq_comm_unique_id": (_int, [_ptr]),
     "tq_comm_init": (_int, [_ptr, _int, _int]),
     "tq_comm_ready": (_int, []),

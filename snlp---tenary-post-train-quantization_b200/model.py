@@ -1,0 +1,270 @@
+"""Ternary inference layer on 2-bit codes -- B200 mirror of the reference's ``model.py`` layer wrappers
+(``/root/reference/model.py``: ``TernaryLinear`` :17-127, ``get_model_layers`` :130-136, ``get_llm_layers``
+:139-159, ``find_linear_layers`` :162-171, ``replace_linear_with_ternary`` :174-225, ``get_model_type`` :268-290,
+``compute_model_size`` :293-303).  SURVEY 8f N2: the consumer of the packed codes.
+
+``TernaryLinear`` keeps the reference's constructor, ``set_quantized_params(alpha, mu, T, perm, bias)``,
+``forward``, ``_dequantize`` and ``memory_footprint``, but
+
+  * stores the codes as 2 bits per weight in sweep order (``codes``, the TL2 layout of include/tq100.h) instead of
+    an int8 matrix (1 byte per weight, model.py:43); ``T`` is a read-only property that unpacks them;
+  * computes ``F.linear(x, Wq)`` with ``Wq = GPTQ.get_quantized_weight()`` (gptq.py:201-230).  The reference's
+    forward (model.py:84-90) gathers the input by ``perm`` AND un-permutes a weight whose T is already stored in
+    original positions (gptq.py:155), which is only right for the identity permutation (pinned in
+    tests/test_ternary_linear_cpu.py against the reference's own outputs).  For ``use_ssr=False`` results the two
+    agree to rounding.
+
+Decode-sized inputs (<= ``gemv_max_tokens`` rows) go through ``tq_tl_gemv`` (reads 0.25 B per weight); larger inputs
+dequantise to a dense weight in the layer dtype (``tq_tl_dequant``) and call the library GEMM, like the reference's
+``_dequantize`` + ``F.linear``.  CUDA only: no CPU fallback.
+
+HF model loading (``load_model_for_quantization``, model.py:228-265) is out of scope (no network).
+"""
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+try:
+    from . import _lib
+except ImportError:
+    import _lib
+
+
+class TernaryLinear(nn.Module):
+    """model.py:17-127 on packed codes."""
+
+    gemv_max_tokens = 16
+
+    def __init__(self, in_features: int, out_features: int, block_size: int = 128, bias: bool = True,
+                 dtype: torch.dtype = torch.float16, device=None):
+        super().__init__()
+        if dtype not in (torch.float32, torch.float16, torch.bfloat16):
+            raise ValueError(f"unsupported layer dtype {dtype}")
+        if block_size <= 0 or block_size % 16 != 0:
+            raise ValueError("TernaryLinear: block_size must be a positive multiple of 16 (a 32-bit code word must "
+                             "not straddle two scale blocks)")
+        self.in_features = in_features
+        self.out_features = out_features
+        self.block_size = block_size
+        num_blocks = (in_features + block_size - 1) // block_size
+        wpr = (in_features + 15) // 16
+        # code 1 = T 0 everywhere (0x55555555), like the reference's zero-initialised T (model.py:43)
+        self.register_buffer("codes", torch.full((out_features, wpr), 0x55555555, dtype=torch.int32, device=device))
+        self.register_buffer("alpha", torch.ones(out_features, num_blocks, dtype=dtype, device=device))
+        self.register_buffer("mu", torch.zeros(out_features, num_blocks, dtype=dtype, device=device))
+        self.register_buffer("perm", torch.arange(in_features, dtype=torch.long, device=device))
+        self.register_buffer("inv_perm", torch.arange(in_features, dtype=torch.long, device=device))
+        if bias:
+            self.register_buffer("bias", torch.zeros(out_features, dtype=dtype, device=device))
+        else:
+            self.bias = None
+        self._derived = None          # (wtab f32 [n, nb, 4], perm int32 or None, bias f32 or None), rebuilt lazily
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
+
+    # ------------------------------------------------------------------ parameters
+    def _invalidate(self):
+        self._derived = None
+
+    def _apply(self, fn, *args, **kwargs):
+        self._invalidate()
+        return super()._apply(fn, *args, **kwargs)
+
+    def set_quantized_params(self, alpha: torch.Tensor, mu: torch.Tensor, T: torch.Tensor, perm: torch.Tensor,
+                             bias: Optional[torch.Tensor] = None):
+        """model.py:58-73.  T is the (n, m) ternary matrix in ORIGINAL column positions as GPTQ.quantize returns it
+        (gptq.py:155), any dtype; it is packed on the device the layer lives on."""
+        lib = _lib.load()
+        dev = self.codes.device
+        _lib.require_cuda(self.codes, "TernaryLinear buffers")
+        n, m = self.out_features, self.in_features
+        if tuple(T.shape) != (n, m) or perm.numel() != m:
+            raise ValueError(f"expected T {(n, m)} and perm ({m},), got {tuple(T.shape)} and {tuple(perm.shape)}")
+        self.alpha.copy_(alpha)
+        self.mu.copy_(mu)
+        self.perm.copy_(perm)
+        self.inv_perm.copy_(torch.argsort(self.perm))
+        T8 = T.detach().to(device=dev).to(torch.int8).contiguous()
+        p32 = self.perm.to(torch.int32).contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(lib.tq_tl_pack(_lib.ptr(T8), n, m, _lib.ptr(p32), _lib.ptr(self.codes), self.codes.shape[1],
+                                      _lib.stream()), "tq_tl_pack")
+        for t in (T8, p32):
+            t.record_stream(torch.cuda.current_stream(dev))
+        if bias is not None and self.bias is not None:
+            self.bias.copy_(bias)
+        self._invalidate()
+
+    def _prepared(self):
+        if self._derived is not None:
+            return self._derived
+        lib = _lib.load()
+        _lib.require_cuda(self.codes, "TernaryLinear buffers")
+        dev = self.codes.device
+        n, nb = self.alpha.shape
+        wtab = torch.empty((n, nb, 4), dtype=torch.float32, device=dev)
+        a32 = self.alpha.float().contiguous()
+        u32 = self.mu.float().contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(lib.tq_tl_wtab(_lib.ptr(a32), _lib.ptr(u32), n, nb, _lib.dtype_code(self.alpha.dtype),
+                                      _lib.ptr(wtab), _lib.stream()), "tq_tl_wtab")
+        for t in (a32, u32):
+            t.record_stream(torch.cuda.current_stream(dev))
+        identity = bool(torch.equal(self.perm, torch.arange(self.in_features, device=dev)))
+        perm32 = None if identity else self.perm.to(torch.int32).contiguous()
+        bias32 = None if self.bias is None else self.bias.float().contiguous()
+        self._derived = (wtab, perm32, bias32)
+        return self._derived
+
+    @property
+    def T(self) -> torch.Tensor:
+        """int8 (n, m) ternary matrix in original column positions (the reference's buffer, model.py:43)."""
+        lib = _lib.load()
+        _lib.require_cuda(self.codes, "TernaryLinear buffers")
+        _, perm32, _ = self._prepared()
+        n, m = self.out_features, self.in_features
+        out = torch.empty((n, m), dtype=torch.int8, device=self.codes.device)
+        with torch.cuda.device(self.codes.device):
+            _lib.check(lib.tq_tl_unpack(_lib.ptr(self.codes), self.codes.shape[1], n, m, _lib.ptr(perm32), _lib.ptr(out),
+                                        _lib.stream()), "tq_tl_unpack")
+        return out
+
+    # ------------------------------------------------------------------ forward
+    def _dequantize(self) -> torch.Tensor:
+        """Dense weight (n, m) in the layer dtype, original column positions (gptq.py:201-230 semantics)."""
+        lib = _lib.load()
+        wtab, perm32, _ = self._prepared()
+        n, m = self.out_features, self.in_features
+        W = torch.empty((n, m), dtype=self.alpha.dtype, device=self.codes.device)
+        with torch.cuda.device(self.codes.device):
+            _lib.check(lib.tq_tl_dequant(_lib.ptr(self.codes), self.codes.shape[1], _lib.ptr(wtab), n, m, self.block_size,
+                                         _lib.ptr(perm32), _lib.ptr(W), _lib.dtype_code(W.dtype), m, _lib.stream()),
+                       "tq_tl_dequant")
+        return W
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """model.py:75-95."""
+        lib = _lib.load()
+        _lib.require_cuda(x, "x")
+        if x.shape[-1] != self.in_features:
+            raise ValueError(f"expected (..., {self.in_features}) input, got {tuple(x.shape)}")
+        lead = x.shape[:-1]
+        x2 = x.reshape(-1, self.in_features)
+        tokens = x2.shape[0]
+        dtype = self.alpha.dtype
+        if tokens > self.gemv_max_tokens:
+            out = torch.nn.functional.linear(x2.to(dtype), self._dequantize(), self.bias)
+            return out.reshape(*lead, self.out_features)
+        wtab, perm32, bias32 = self._prepared()
+        if x2.dtype not in (torch.float32, torch.float16, torch.bfloat16):
+            x2 = x2.to(dtype)
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        y = torch.empty((tokens, self.out_features), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(lib.tq_tl_gemv(_lib.ptr(self.codes), self.codes.shape[1], _lib.ptr(wtab), self.out_features,
+                                      self.in_features, self.block_size, _lib.ptr(x2), _lib.dtype_code(x2.dtype),
+                                      x2.stride(0) if tokens > 1 else self.in_features, tokens, _lib.ptr(perm32),
+                                      _lib.ptr(bias32), _lib.ptr(y), self.out_features, _lib.stream()), "tq_tl_gemv")
+        x2.record_stream(torch.cuda.current_stream(x.device))
+        return y.to(dtype).reshape(*lead, self.out_features)
+
+    def memory_footprint(self) -> int:
+        """Bytes this layer keeps resident (model.py:112-127 counts an int8 T and an int64 perm; here the codes are
+        2 bits per weight and the kernels read perm as int32)."""
+        codes = self.codes.numel() * 4
+        scales = (self.alpha.numel() + self.mu.numel()) * self.alpha.element_size()
+        perm = self.perm.numel() * 4
+        bias = self.bias.numel() * self.bias.element_size() if self.bias is not None else 0
+        return codes + scales + perm + bias
+
+    def extra_repr(self) -> str:
+        return (f"in_features={self.in_features}, out_features={self.out_features}, block_size={self.block_size}, "
+                f"bias={self.bias is not None}, dtype={self.alpha.dtype}, codes=2-bit")
+
+
+# ---------------------------------------------------------------------- model walkers (pure Python)
+def get_model_layers(model: nn.Module) -> Dict[str, nn.Linear]:
+    """model.py:130-136: every nn.Linear by qualified name."""
+    return {name: mod for name, mod in model.named_modules() if isinstance(mod, nn.Linear)}
+
+
+_LAYER_PATHS = {
+    "llama": ("model.layers",), "llama2": ("model.layers",), "llama3": ("model.layers",),
+    "qwen": ("model.layers",), "qwen3": ("model.layers",),
+    "gemma": ("language_model.layers", "model.layers"), "gemma3": ("language_model.layers", "model.layers"),
+    "opt": ("model.decoder.layers",),
+    "bloom": ("transformer.h",),
+}
+
+
+def get_llm_layers(model: nn.Module, model_type: str = "llama") -> List[nn.Module]:
+    """model.py:139-159: the list of transformer blocks of a HF causal LM."""
+    if model_type not in _LAYER_PATHS:
+        raise ValueError(f"Unknown model type: {model_type}")
+    for path in _LAYER_PATHS[model_type]:
+        obj = model
+        try:
+            for part in path.split("."):
+                obj = getattr(obj, part)
+        except AttributeError:
+            continue
+        return obj
+    raise AttributeError(f"Cannot find layers in {model_type} model")
+
+
+def find_linear_layers(module: nn.Module, prefix: str = "") -> Dict[str, nn.Linear]:
+    """model.py:162-171: nn.Linear children, recursively, keyed by dotted path below `module`."""
+    found = {}
+    for name, child in module.named_children():
+        path = f"{prefix}.{name}" if prefix else name
+        if isinstance(child, nn.Linear):
+            found[path] = child
+        else:
+            found.update(find_linear_layers(child, path))
+    return found
+
+
+def replace_linear_with_ternary(model: nn.Module, quantized_params: Dict[str, Dict[str, torch.Tensor]],
+                                block_size: int = 128) -> nn.Module:
+    """model.py:174-225: swap every named nn.Linear for a TernaryLinear holding its quantised parameters."""
+    for name, params in quantized_params.items():
+        *parents, leaf = name.split(".")
+        parent = model
+        for part in parents:
+            parent = getattr(parent, part)
+        old = getattr(parent, leaf)
+        new = TernaryLinear(old.in_features, old.out_features, block_size=block_size, bias=old.bias is not None,
+                            dtype=params["alpha"].dtype, device=old.weight.device)
+        new.set_quantized_params(params["alpha"], params["mu"], params["T"], params["perm"],
+                                 old.bias.data if old.bias is not None else None)
+        setattr(parent, leaf, new)
+        del old
+    return model
+
+
+_TYPE_KEYS = (("gemma-3", "gemma3"), ("gemma3", "gemma3"), ("gemma", "gemma"), ("llama-3", "llama3"),
+              ("llama3", "llama3"), ("llama-2", "llama2"), ("llama2", "llama2"), ("llama", "llama"),
+              ("qwen3", "qwen3"), ("qwen", "qwen"), ("opt", "opt"), ("bloom", "bloom"))
+
+
+def get_model_type(model_name: str) -> str:
+    """model.py:268-290: first matching family key in the lower-cased name; 'llama' when nothing matches."""
+    low = model_name.lower()
+    for key, family in _TYPE_KEYS:
+        if key in low:
+            return family
+    return "llama"
+
+
+def compute_model_size(model: nn.Module, quantized: bool = False) -> float:
+    """model.py:293-303: parameters + buffers in GiB."""
+    total = sum(p.numel() * p.element_size() for p in model.parameters())
+    total += sum(b.numel() * b.element_size() for b in model.buffers())
+    return total / (1024 ** 3)
+
+
+def compute_compression_ratio(original_size: float, quantized_size: float) -> float:
+    """model.py:306-308."""
+    return original_size / quantized_size

@@ -43,3 +43,54 @@ def unpack_ternary(packed: torch.Tensor, orig_shape: Tuple[int, ...]) -> torch.T
     with torch.cuda.device(packed.device):
         _lib.check(lib.tq_unpack2b(_lib.ptr(p), total, _lib.ptr(out), _lib.stream()), "tq_unpack2b")
     return out.reshape(orig_shape)
+
+
+# ---------------------------------------------------------------------- model-level helpers (host only)
+def set_seed(seed: int):
+    """utils.py:15-21."""
+    import random
+    import numpy as np
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+
+
+def compute_bits_per_weight(model: torch.nn.Module, include_scales: bool = True) -> float:
+    """utils.py:251-285: 1.58 bits per ternary weight + 16 bits per alpha/mu entry over every ternary layer;
+    16.0 for a model without one.  (The codes are stored at 2 bits per weight; ``stored_bits_per_weight`` reports
+    what the buffers really occupy.)"""
+    weights = 0
+    bits = 0.0
+    for module in model.modules():
+        if hasattr(module, "codes") and hasattr(module, "alpha") and hasattr(module, "mu"):
+            count = module.out_features * module.in_features
+            weights += count
+            bits += count * 1.58
+            if include_scales:
+                bits += (module.alpha.numel() + module.mu.numel()) * 16
+    return bits / weights if weights else 16.0
+
+
+def stored_bits_per_weight(model: torch.nn.Module) -> float:
+    """Resident bits per weight of the ternary layers (2-bit codes, scales, int32 permutation, bias)."""
+    weights = 0
+    nbytes = 0
+    for module in model.modules():
+        if hasattr(module, "codes") and hasattr(module, "memory_footprint"):
+            weights += module.out_features * module.in_features
+            nbytes += module.memory_footprint()
+    return 8.0 * nbytes / weights if weights else 16.0
+
+
+def save_quantized_model(model: torch.nn.Module, save_path: str, quantized_params):
+    """utils.py:288-296: one file holding the state dict and the per-layer parameter dicts."""
+    torch.save({"model_state_dict": model.state_dict(), "quantized_params": quantized_params}, save_path)
+
+
+def load_quantized_model(model: torch.nn.Module, load_path: str):
+    """utils.py:299-304."""
+    checkpoint = torch.load(load_path, map_location="cpu")
+    model.load_state_dict(checkpoint["model_state_dict"])
+    return model, checkpoint.get("quantized_params", {})
