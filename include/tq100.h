@@ -197,6 +197,10 @@ int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const float* Hd,
  *   tq_tl_gemv     y[t, r] = sum_p wtab[r, p/block][code(r,p)] * x[t, perm[p]] (+ bias[r]) for M tokens, i.e.
  *                  model.py:75-95 with the dequantised weight of gptq.py:201-230; x [M, ldx] of xdtype, y f32
  *                  [M, ldy]; meant for decode-sized M (4 tokens per launch)
+ *   tq_tl_gemm_tc  the same product for MANY tokens as one tcgen05 GEMM that expands the codes to the layer's 16-bit
+ *                  dtype in shared memory (no dense weight in HBM): x, y [M, ld] of xdtype (TQ_F16 / TQ_BF16 = the layer
+ *                  dtype wtab was built for), fp32 accumulation; needs m % 8 == 0 and 16-byte aligned x; xperm_work
+ *                  [M, m] of xdtype is the gather buffer for x[:, perm] (model.py:84), unused when perm is NULL
  *   tq_tl_dequant  dense Wq [n, ldw] of wdtype in ORIGINAL column positions (model.py:97-110 / gptq.py:201-230)
  *   tq_tl_unpack   T int8 [n, m] in original positions */
 int64_t tq_tl_words_per_row(int64_t m);
@@ -206,6 +210,9 @@ int tq_tl_wtab(const float* alpha, const float* mu, int64_t n, int64_t nb, int w
 int tq_tl_gemv(const uint32_t* codes, int64_t wpr, const float* wtab, int64_t n, int64_t m, int64_t block,
                const void* x, int xdtype, int64_t ldx, int64_t M, const int32_t* perm, const float* bias,
                float* y, int64_t ldy, void* stream);
+int tq_tl_gemm_tc(const uint32_t* codes, int64_t wpr, const float* wtab, int64_t n, int64_t m, int64_t block,
+                  const void* x, int xdtype, int64_t ldx, int64_t M, const int32_t* perm, void* xperm_work,
+                  const float* bias, void* y, int64_t ldy, void* stream);
 int tq_tl_dequant(const uint32_t* codes, int64_t wpr, const float* wtab, int64_t n, int64_t m, int64_t block,
                   const int32_t* perm, void* W, int wdtype, int64_t ldw, void* stream);
 int tq_tl_unpack(const uint32_t* codes, int64_t wpr, int64_t n, int64_t m, const int32_t* perm, int8_t* Torig,

@@ -10,7 +10,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "_build")
 LIB = os.path.join(PKG, "libtq100.so")
-SOURCES = ["api", "hessian_ffma", "hessian_tc", "cholinv", "atq", "ssr", "feedback", "codec", "sweep", "comm", "gemm_tc", "ternary_linear"]
+SOURCES = ["api", "hessian_ffma", "hessian_tc", "cholinv", "atq", "ssr", "feedback", "codec", "sweep", "comm", "gemm_tc", "ternary_linear", "ternary_gemm_tc"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC"]

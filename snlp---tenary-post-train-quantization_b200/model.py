@@ -14,9 +14,10 @@
     tests/test_ternary_linear_cpu.py against the reference's own outputs).  For ``use_ssr=False`` results the two
     agree to rounding.
 
-Decode-sized inputs (<= ``gemv_max_tokens`` rows) go through ``tq_tl_gemv`` (reads 0.25 B per weight); larger inputs
-dequantise to a dense weight in the layer dtype (``tq_tl_dequant``) and call the library GEMM, like the reference's
-``_dequantize`` + ``F.linear``.  CUDA only: no CPU fallback.
+Decode-sized inputs (<= ``gemv_max_tokens`` rows) go through ``tq_tl_gemv`` (reads 0.25 B per weight).  Larger
+inputs either run ``tq_tl_gemm_tc`` -- one tcgen05 GEMM that expands the codes to the layer's 16-bit dtype in shared
+memory (``fused_gemm``) -- or dequantise to a dense weight in the layer dtype (``tq_tl_dequant``) and call the library
+GEMM, like the reference's ``_dequantize`` + ``F.linear`` (fp32 layers always do).  CUDA only: no CPU fallback.
 
 HF model loading (``load_model_for_quantization``, model.py:228-265) is out of scope (no network).
 """
@@ -36,6 +37,7 @@ class TernaryLinear(nn.Module):
     """model.py:17-127 on packed codes."""
 
     gemv_max_tokens = 16
+    fused_gemm = False            # many-token path: True = tq_tl_gemm_tc (fp16/bf16 layers), False = dense weight + library GEMM
 
     def __init__(self, in_features: int, out_features: int, block_size: int = 128, bias: bool = True,
                  dtype: torch.dtype = torch.float16, device=None):
@@ -90,8 +92,6 @@ class TernaryLinear(nn.Module):
         with torch.cuda.device(dev):
             _lib.check(lib.tq_tl_pack(_lib.ptr(T8), n, m, _lib.ptr(p32), _lib.ptr(self.codes), self.codes.shape[1],
                                       _lib.stream()), "tq_tl_pack")
-        for t in (T8, p32):
-            t.record_stream(torch.cuda.current_stream(dev))
         if bias is not None and self.bias is not None:
             self.bias.copy_(bias)
         self._invalidate()
@@ -109,8 +109,6 @@ class TernaryLinear(nn.Module):
         with torch.cuda.device(dev):
             _lib.check(lib.tq_tl_wtab(_lib.ptr(a32), _lib.ptr(u32), n, nb, _lib.dtype_code(self.alpha.dtype),
                                       _lib.ptr(wtab), _lib.stream()), "tq_tl_wtab")
-        for t in (a32, u32):
-            t.record_stream(torch.cuda.current_stream(dev))
         identity = bool(torch.equal(self.perm, torch.arange(self.in_features, device=dev)))
         perm32 = None if identity else self.perm.to(torch.int32).contiguous()
         bias32 = None if self.bias is None else self.bias.float().contiguous()
@@ -154,6 +152,8 @@ class TernaryLinear(nn.Module):
         tokens = x2.shape[0]
         dtype = self.alpha.dtype
         if tokens > self.gemv_max_tokens:
+            if self.fused_gemm and dtype != torch.float32 and self.in_features % 8 == 0:
+                return self._forward_fused(x2.to(dtype)).reshape(*lead, self.out_features)
             out = torch.nn.functional.linear(x2.to(dtype), self._dequantize(), self.bias)
             return out.reshape(*lead, self.out_features)
         wtab, perm32, bias32 = self._prepared()
@@ -167,8 +167,23 @@ class TernaryLinear(nn.Module):
                                       self.in_features, self.block_size, _lib.ptr(x2), _lib.dtype_code(x2.dtype),
                                       x2.stride(0) if tokens > 1 else self.in_features, tokens, _lib.ptr(perm32),
                                       _lib.ptr(bias32), _lib.ptr(y), self.out_features, _lib.stream()), "tq_tl_gemv")
-        x2.record_stream(torch.cuda.current_stream(x.device))
         return y.to(dtype).reshape(*lead, self.out_features)
+
+    def _forward_fused(self, x2: torch.Tensor) -> torch.Tensor:
+        """Many tokens, 16-bit layer: one tcgen05 GEMM that expands the codes in shared memory (tq_tl_gemm_tc)."""
+        lib = _lib.load()
+        wtab, perm32, bias32 = self._prepared()
+        if x2.stride(-1) != 1 or (x2.stride(0) * 2) % 16 != 0 or x2.data_ptr() % 16 != 0:
+            x2 = x2.contiguous()
+        tokens = x2.shape[0]
+        y = torch.empty((tokens, self.out_features), dtype=x2.dtype, device=x2.device)
+        work = None if perm32 is None else torch.empty((tokens, self.in_features), dtype=x2.dtype, device=x2.device)
+        with torch.cuda.device(x2.device):
+            _lib.check(lib.tq_tl_gemm_tc(_lib.ptr(self.codes), self.codes.shape[1], _lib.ptr(wtab), self.out_features,
+                                         self.in_features, self.block_size, _lib.ptr(x2), _lib.dtype_code(x2.dtype),
+                                         x2.stride(0), tokens, _lib.ptr(perm32), _lib.ptr(work), _lib.ptr(bias32),
+                                         _lib.ptr(y), self.out_features, _lib.stream()), "tq_tl_gemm_tc")
+        return y
 
     def memory_footprint(self) -> int:
         """Bytes this layer keeps resident (model.py:112-127 counts an int8 T and an int64 perm; here the codes are
