@@ -187,16 +187,16 @@ int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const float* Hd,
 
 /* ---- SURVEY 8f N2  TernaryLinear on 2-bit codes, model.py:17-127 -----------------------------------
  * Layer format: codes u32 [n, wpr] (wpr >= tq_tl_words_per_row(m) = ceil(m/16)): word w of row r holds SWEEP
- * positions 16w..16w+15, position p at bits 2(p%16)..+1, code = T[r, perm[p]] + 1 (utils.py:203 coding),
- * positions >= m = code 1; so block k of alpha/mu (gptq.py:153-155) covers positions [k*block, (k+1)*block).
+ * positions 16w..16w+15 as two bit planes -- bit j = 1 iff T[r, perm[16w+j]] = +1, bit 16+j = 1 iff it is -1,
+ * positions >= m are 0 in both -- so block k of alpha/mu (gptq.py:153-155) covers positions [k*block, (k+1)*block).
  * wtab f32 [n, nb, 4] = (fl(mu-alpha), mu, fl(alpha+mu), 0): `alpha * T + mu` of model.py:108 evaluated and
- * rounded in the layer dtype `wdtype` (TQ_F32/F16/BF16), indexed by code.  perm NULL = identity.
+ * rounded in the layer dtype `wdtype` (TQ_F32/F16/BF16), for T = -1, 0, +1.  perm NULL = identity.
  * block must be a multiple of 16 (else TQ_E_UNSUPPORTED).
  *   tq_tl_pack     T int8 [n, m] in ORIGINAL positions (gptq.py:155) + perm -> codes
  *   tq_tl_wtab     alpha, mu f32 [n, nb] -> wtab
- *   tq_tl_gemv     y[t, r] = sum_p wtab[r, p/block][code(r,p)] * x[t, perm[p]] (+ bias[r]) for M tokens, i.e.
+ *   tq_tl_gemv     y[t, r] = sum_p wtab[r, p/block][T(r,p)] * x[t, perm[p]] (+ bias[r]) for M tokens, i.e.
  *                  model.py:75-95 with the dequantised weight of gptq.py:201-230; x [M, ldx] of xdtype, y f32
- *                  [M, ldy]; meant for decode-sized M (4 tokens per launch)
+ *                  [M, ldy]; meant for decode-sized M (4 tokens per launch; subset sums of x looked up by nibble)
  *   tq_tl_gemm_tc  the same product for MANY tokens as one tcgen05 GEMM that expands the codes to the layer's 16-bit
  *                  dtype in shared memory (no dense weight in HBM): x, y [M, ld] of xdtype (TQ_F16 / TQ_BF16 = the layer
  *                  dtype wtab was built for), fp32 accumulation; needs m % 8 == 0 and 16-byte aligned x; xperm_work

@@ -84,18 +84,20 @@ def forward_reference(x, alpha, mu, T, perm, bias=None, block_size=128, dtype="f
 
 
 def pack_layer(T, perm):
-    """TL2 codes: uint32 [n, ceil(m/16)]; word w of row r holds sweep positions 16w..16w+15, position p at bits
-    2(p%16)..+1, code = T[r, perm[p]] + 1 (utils.py:203 coding); positions >= m hold code 1.  Bit-exact bar."""
+    """TL2 codes: uint32 [n, ceil(m/16)]; word w of row r holds sweep positions 16w..16w+15 as two bit planes:
+    bit j = 1 iff T[r, perm[16w+j]] = +1, bit 16+j = 1 iff it is -1 (neither: 0); positions >= m hold 0.
+    Bit-exact bar."""
     T = np.asarray(T).astype(np.int64)
     n, m = T.shape
     perm = np.asarray(perm, dtype=np.int64)
     wpr = (m + 15) // 16
-    c = np.ones((n, wpr * 16), dtype=np.uint32)
-    c[:, :m] = (T[:, perm] + 1).astype(np.uint32)
-    c = c.reshape(n, wpr, 16)
+    Tp = np.zeros((n, wpr * 16), dtype=np.int64)
+    Tp[:, :m] = T[:, perm]
+    Tp = Tp.reshape(n, wpr, 16)
     words = np.zeros((n, wpr), dtype=np.uint32)
     for j in range(16):
-        words |= c[:, :, j] << np.uint32(2 * j)
+        words |= (Tp[:, :, j] == 1).astype(np.uint32) << np.uint32(j)
+        words |= (Tp[:, :, j] == -1).astype(np.uint32) << np.uint32(16 + j)
     return words
 
 
@@ -106,7 +108,9 @@ def unpack_layer(words, m, perm):
     perm = np.asarray(perm, dtype=np.int64)
     c = np.empty((n, wpr, 16), dtype=np.int8)
     for j in range(16):
-        c[:, :, j] = ((words >> np.uint32(2 * j)) & np.uint32(3)).astype(np.int8) - 1
+        plus = ((words >> np.uint32(j)) & np.uint32(1)).astype(np.int8)
+        minus = ((words >> np.uint32(16 + j)) & np.uint32(1)).astype(np.int8)
+        c[:, :, j] = plus - minus
     Tp = c.reshape(n, wpr * 16)[:, :m]
     T = np.empty((n, m), dtype=np.int8)
     T[:, perm] = Tp

@@ -3,13 +3,14 @@
 // every forward, model.py:87, :97-110).
 //
 //   D[128 weight rows, 256 tokens] (fp32, TMEM) += A[128 x 64] * B[256 x 64]',  kind::f16, UMMA 128x256x16
+//   (128-token tiles, UMMA 128x128x16, when 256-token tiles would leave SMs without work)
 //   A = dequantised weights, K-major, 128B-swizzled, WRITTEN BY EIGHT DEQUANT WARPS from the TL2 code words
 //       (ternary_linear.cu): value = wtab[row, p/block][code], already rounded to the layer's 16-bit dtype, so the
 //       tensor core multiplies exactly the reference's fp16/bf16 weight `alpha * T + mu`;
 //   B = activations [tokens, m] in sweep order (gathered by perm beforehand when perm is not the identity,
 //       model.py:84), K-major, fetched by TMA (one 256 x 64 box per stage, out-of-range rows/columns zero-filled);
-//   pipeline: 4 smem stages x (A 16 KB + B 32 KB); per stage two "full" barriers (TMA bytes; 256 dequant-thread
-//       arrivals after fence.proxy.async) and one "empty" barrier (tcgen05.commit) that both producers wait on;
+//   pipeline: 4 smem stages x (A 16 KB + B 32 KB); per stage two "full" barriers (TMA bytes; one arrival per
+//       dequant warp after every lane's fence.proxy.async) and one "empty" barrier (tcgen05.commit) that both producers wait on;
 //   TMEM: 2 accumulators x 256 columns, so the epilogue of one tile overlaps the MMAs of the next;
 //   epilogue: tcgen05.ld -> (+ bias) -> 16-bit stores y[token, row] with lanes along the rows (contiguous in y);
 //   schedule: persistent CTAs; tiles ordered token-tile-major so concurrently running CTAs share the same x slab in L2.
@@ -18,12 +19,12 @@
 
 namespace tq {
 
-constexpr int TG_BM = 128, TG_BN = 256, TG_BK = 64, TG_STAGES = 4, TG_UMMA_K = 16;
+constexpr int TG_BM = 128, TG_BK = 64, TG_STAGES = 4, TG_UMMA_K = 16;
 constexpr int TG_A_BYTES = TG_BM * TG_BK * 2;                 // 16384
-constexpr int TG_B_BYTES = TG_BN * TG_BK * 2;                 // 32768
-constexpr int TG_STAGE_BYTES = TG_A_BYTES + TG_B_BYTES;       // 49152
+constexpr int TG_STAGE_BYTES = TG_A_BYTES + 256 * TG_BK * 2;  // 49152: A + the widest B tile (256 tokens)
 constexpr int TG_THREADS = 512;
 constexpr int TG_DEQ_THREADS = 256;
+constexpr int TG_DEQ_WARPS = TG_DEQ_THREADS / 32;
 constexpr int TG_SMEM = TG_STAGES * TG_STAGE_BYTES + 256 + 1024;
 
 struct TgProblem {
@@ -31,6 +32,7 @@ struct TgProblem {
     int64_t wpr;
     const float4* wtab;
     int n, m, nb, block, M;
+    int wpb, wpb_shift;              // code words per scale block (block / 16); its log2 when a power of two, else -1
     int row_tiles, tok_tiles, ksteps;
     const float* bias;
     void* y;
@@ -50,18 +52,19 @@ template <typename HT> __device__ __forceinline__ HT tg_out(float v);
 template <> __device__ __forceinline__ __half tg_out<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __nv_bfloat16 tg_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
-// 16 codes of one word -> 8 packed pairs of 16-bit weights (position 2i in the low half of q[i])
+// the 16 positions of one code word (bit j: +1, bit 16+j: -1) -> 8 packed pairs of 16-bit weights (position 2i in
+// the low half of q[i]); h0/h1/h2 = bit patterns of w-, w0, w+
 __device__ __forceinline__ void tg_expand_word(uint32_t word, uint32_t h0, uint32_t h1, uint32_t h2, uint32_t (&q)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const uint32_t ca = (word >> (4 * i)) & 3u, cb = (word >> (4 * i + 2)) & 3u;
-        const uint32_t lo = ca == 0u ? h0 : (ca == 1u ? h1 : h2);
-        const uint32_t hi = cb == 0u ? h0 : (cb == 1u ? h1 : h2);
+        const uint32_t lo = (word & (1u << (2 * i))) ? h2 : ((word & (1u << (16 + 2 * i))) ? h0 : h1);
+        const uint32_t hi = (word & (1u << (2 * i + 1))) ? h2 : ((word & (1u << (17 + 2 * i))) ? h0 : h1);
         q[i] = lo | (hi << 16);
     }
 }
 
-template <typename HT>
+// TG_BN = tokens per tile: 256, or 128 when 256-token tiles would leave SMs without work
+template <typename HT, int TG_BN>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tl_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TgProblem p, uint32_t idesc) {
     extern __shared__ uint8_t smem_raw[];
@@ -80,7 +83,7 @@ tl_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TgProblem p, 
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < TG_STAGES; ++s) {
             mbar_init(fullx_bar(s), 1);
-            mbar_init(fullw_bar(s), TG_DEQ_THREADS);
+            mbar_init(fullw_bar(s), TG_DEQ_WARPS);
             mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
@@ -92,6 +95,7 @@ tl_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TgProblem p, 
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int tiles = p.row_tiles * p.tok_tiles;
+    constexpr int TG_B_BYTES = TG_BN * TG_BK * 2;
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer: activations =====
@@ -159,6 +163,8 @@ tl_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TgProblem p, 
         }
     } else if (warp >= 8) {
         // ===== dequant producers: thread = (row of the tile, half of the 64-wide K slab = 2 code words) =====
+        // Code words and their weight-table entries are fetched TWO slabs ahead of the one being expanded: with one
+        // CTA per SM nothing else hides the L2 latency of these loads.
         const int dt = threadIdx.x - 256;
         const int row = dt >> 1, h = dt & 1;
         const int words = (p.m + 15) >> 4;
@@ -169,34 +175,27 @@ tl_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TgProblem p, 
             const bool live = r < p.n;
             const uint32_t* crow = p.codes + (int64_t)(live ? r : 0) * p.wpr;
             const float4* trow = p.wtab + (int64_t)(live ? r : 0) * p.nb;
-            uint32_t w0 = 0, w1 = 0;
-            {
-                const int w = 2 * h;
-                if (live && w < words) w0 = __ldg(crow + w);
-                if (live && w + 1 < words) w1 = __ldg(crow + w + 1);
-            }
+            const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            auto blk_of = [&](int w) { return p.wpb_shift >= 0 ? (w >> p.wpb_shift) : (w / p.wpb); };
+            auto fetch = [&](int ks, uint32_t& a, uint32_t& b, float4& ta, float4& tb) {
+                const int w = ks * 4 + 2 * h;
+                a = 0u; b = 0u; ta = zero4; tb = zero4;            // out of range: zeros in both planes AND a zero table
+                if (live && ks < p.ksteps) {
+                    if (w < words) { a = __ldg(crow + w); ta = __ldg(trow + min(blk_of(w), p.nb - 1)); }
+                    if (w + 1 < words) { b = __ldg(crow + w + 1); tb = __ldg(trow + min(blk_of(w + 1), p.nb - 1)); }
+                }
+            };
+            uint32_t w0, w1, n0, n1;
+            float4 ta, tb, na, nb4;
+            fetch(0, w0, w1, ta, tb);
+            fetch(1, n0, n1, na, nb4);
             for (int ks = 0; ks < p.ksteps; ++ks) {
-                const int w = ks * 4 + 2 * h;                // first of this thread's two words in the slab
-                uint32_t n0 = 0, n1 = 0;                     // next slab's words: in flight while this slab is expanded
-                if (ks + 1 < p.ksteps) {
-                    if (live && w + 4 < words) n0 = __ldg(crow + w + 4);
-                    if (live && w + 5 < words) n1 = __ldg(crow + w + 5);
-                }
+                uint32_t f0, f1;
+                float4 fa, fb;
+                fetch(ks + 2, f0, f1, fa, fb);
                 uint32_t qa[8], qb[8];
-                if (live && w < words) {
-                    const float4 wt = __ldg(trow + min((w * 16) / p.block, p.nb - 1));
-                    tg_expand_word(w0, tg_bits<HT>(wt.x), tg_bits<HT>(wt.y), tg_bits<HT>(wt.z), qa);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) qa[i] = 0u;
-                }
-                if (live && w + 1 < words) {
-                    const float4 wt = __ldg(trow + min(((w + 1) * 16) / p.block, p.nb - 1));
-                    tg_expand_word(w1, tg_bits<HT>(wt.x), tg_bits<HT>(wt.y), tg_bits<HT>(wt.z), qb);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) qb[i] = 0u;
-                }
+                tg_expand_word(w0, tg_bits<HT>(ta.x), tg_bits<HT>(ta.y), tg_bits<HT>(ta.z), qa);
+                tg_expand_word(w1, tg_bits<HT>(tb.x), tg_bits<HT>(tb.y), tg_bits<HT>(tb.z), qb);
                 mbar_wait(empty_bar(stage), phase ^ 1);
                 const uint32_t srow = s_base + stage * TG_STAGE_BYTES + row * 128;
                 const int c0 = 4 * h;                        // this thread's four 16-byte chunks of the 128-byte row
@@ -209,9 +208,10 @@ tl_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TgProblem p, 
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((c0 + 3) ^ (row & 7)) << 4)),
                              "r"(qb[4]), "r"(qb[5]), "r"(qb[6]), "r"(qb[7]) : "memory");
                 fence_proxy_async_smem();                    // generic-proxy writes -> visible to the tensor core's async proxy
-                mbar_arrive(fullw_bar(stage));
-                w0 = n0;
-                w1 = n1;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(fullw_bar(stage)); // one arrival per warp: 256 arrivals on one barrier serialise
+                w0 = n0; w1 = n1; ta = na; tb = nb4;
+                n0 = f0; n1 = f1; na = fa; nb4 = fb;
                 if (++stage == TG_STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -269,9 +269,13 @@ extern "C" int tq_tl_gemm_tc(const uint32_t* codes, int64_t wpr, const float* wt
         set_error("tq_tl_gemm_tc: activations need a 16-byte aligned base and row pitch (m %% 8 == 0) for TMA");
         return TQ_E_UNSUPPORTED;
     }
+    const int sms = sm_count();
+    // 256-token tiles halve the dequantisation work per MMA; fall back to 128 when they would leave SMs idle
+    const bool wide = ceil_div(n, TG_BM) * ceil_div(M, 256) >= sms || M > 128 && ceil_div(n, TG_BM) * ceil_div(M, 128) > 2 * sms;
+    const int bn = wide ? 256 : 128;
     CUtensorMap map_x;
     int rc = make_tmap_2d(&map_x, xdtype == TQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, xs,
-                          M, m, lds, TG_BN, TG_BK, "tq_tl_gemm_tc(x)");
+                          M, m, lds, bn, TG_BK, "tq_tl_gemm_tc(x)");
     if (rc) return rc;
 
     TgProblem p;
@@ -279,25 +283,36 @@ extern "C" int tq_tl_gemm_tc(const uint32_t* codes, int64_t wpr, const float* wt
     p.wpr = wpr;
     p.wtab = reinterpret_cast<const float4*>(wtab);
     p.n = (int)n; p.m = (int)m; p.nb = (int)ceil_div(m, block); p.block = (int)block; p.M = (int)M;
+    p.wpb = (int)(block / 16);
+    p.wpb_shift = -1;
+    for (int sft = 0; sft < 20; ++sft)
+        if ((1 << sft) == p.wpb) p.wpb_shift = sft;
     p.row_tiles = (int)ceil_div(n, TG_BM);
-    p.tok_tiles = (int)ceil_div(M, TG_BN);
+    p.tok_tiles = (int)ceil_div(M, bn);
     p.ksteps = (int)ceil_div(m, TG_BK);
     p.bias = bias;
     p.y = y;
     p.ldy = ldy;
     const uint32_t fmt = (xdtype == TQ_F16) ? 0u : 1u;
-    // tcgen05 instruction descriptor (kind::f16): D = f32, A/B format, both K-major, N = 256, M = 128
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(TG_BN >> 3) << 17) | ((uint32_t)(TG_BM >> 4) << 24);
+    // tcgen05 instruction descriptor (kind::f16): D = f32, A/B format, both K-major, N = tokens per tile, M = 128
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TG_BM >> 4) << 24);
     const int64_t tiles = (int64_t)p.row_tiles * p.tok_tiles;
-    const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
+    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
     static bool attr_set = false;
     if (!attr_set) {
-        TQ_CUDA(cudaFuncSetAttribute(tl_gemm_tc_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
-        TQ_CUDA(cudaFuncSetAttribute(tl_gemm_tc_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+        TQ_CUDA(cudaFuncSetAttribute(tl_gemm_tc_kernel<__half, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+        TQ_CUDA(cudaFuncSetAttribute(tl_gemm_tc_kernel<__half, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+        TQ_CUDA(cudaFuncSetAttribute(tl_gemm_tc_kernel<__nv_bfloat16, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+        TQ_CUDA(cudaFuncSetAttribute(tl_gemm_tc_kernel<__nv_bfloat16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
         attr_set = true;
     }
-    if (xdtype == TQ_F16) tl_gemm_tc_kernel<__half><<<grid, TG_THREADS, TG_SMEM, st>>>(map_x, p, idesc);
-    else tl_gemm_tc_kernel<__nv_bfloat16><<<grid, TG_THREADS, TG_SMEM, st>>>(map_x, p, idesc);
+    if (xdtype == TQ_F16) {
+        if (wide) tl_gemm_tc_kernel<__half, 256><<<grid, TG_THREADS, TG_SMEM, st>>>(map_x, p, idesc);
+        else tl_gemm_tc_kernel<__half, 128><<<grid, TG_THREADS, TG_SMEM, st>>>(map_x, p, idesc);
+    } else {
+        if (wide) tl_gemm_tc_kernel<__nv_bfloat16, 256><<<grid, TG_THREADS, TG_SMEM, st>>>(map_x, p, idesc);
+        else tl_gemm_tc_kernel<__nv_bfloat16, 128><<<grid, TG_THREADS, TG_SMEM, st>>>(map_x, p, idesc);
+    }
     TQ_LAUNCH_CHECK("tl_gemm_tc_kernel");
     return 0;
 }

@@ -1,33 +1,36 @@
-// the consumer of the packed codes -- the reference's TernaryLinear (model.py:17-127) on 2-bit codes.
+// the consumer of the packed codes -- the reference's TernaryLinear (model.py:17-127) on 2 bits per weight.
 //
-// Layer format ("TL2"), chosen so that one 32-bit word never straddles a scale block:
-//   codes  u32 [n, wpr], wpr >= ceil(m/16): word w of row r holds sweep positions 16w .. 16w+15, position p at
-//          bits 2(p%16) .. +1, code = T[r, perm[p]] + 1 (utils.py:203 coding); positions >= m hold code 1 (T = 0).
+// Layer format ("TL2"), chosen so that one 32-bit word never straddles a scale block and so that subset sums of the
+// input can be looked up by nibble:
+//   codes  u32 [n, wpr], wpr >= ceil(m/16): word w of row r holds sweep positions 16w .. 16w+15 as two bit planes:
+//          bit j = 1 iff T[r, perm[16w+j]] = +1, bit 16+j = 1 iff it is -1; positions >= m hold 0 in both planes.
 //          Sweep order, not original order: block k of alpha/mu (gptq.py:153-155) then covers the contiguous
 //          positions [k*block, (k+1)*block) and the input is gathered once by perm (model.py:84's x[..., perm]).
 //   wtab   f32 [n, nb, 4]: the three values a weight of (row, block) can take, rounded like the reference's
 //          dequantisation `alpha * T + mu` evaluated in the layer dtype (model.py:106-108):
-//          (fl(mu - alpha), mu, fl(alpha + mu), 0) indexed by code.
-// With them  y[t, r] = sum_p wtab[r, p/block][code(r, p)] * x[t, perm[p]]  is exactly F.linear(x, Wq) with
-// Wq = get_quantized_weight (gptq.py:201-230) up to summation order.  (model.py:84-90 permutes the input AND
-// un-permutes W while its T is stored in original positions -- SURVEY Q11 -- so the reference's forward equals this
-// only for the identity permutation; tests pin both facts.)
+//          (w- = fl(mu - alpha), w0 = mu, w+ = fl(alpha + mu), 0).
+// With them  y[t, r] = sum_p w[r, p/block][T(r,p)] * x[t, perm[p]]  is F.linear(x, Wq) with
+// Wq = get_quantized_weight (gptq.py:201-230).  (model.py:84-90 permutes the input AND un-permutes W while its T is
+// stored in original positions -- SURVEY Q11 -- so the reference's forward equals this only for the identity
+// permutation; tests pin both facts.)
 //
 // Kernels (CUDA cores; the codes are 0.25 B per weight, so a decode-sized call is bound by reading them once):
-//   tl_pack_kernel     int8 T in original positions + perm -> codes                       (HBM: n*m in, n*m/4 out)
+//   tl_pack_kernel     int8 T in original positions + perm -> codes
 //   tl_wtab_kernel     alpha, mu -> wtab
-//   tl_gemv_kernel     <= 4 tokens per launch: gathered x staged in shared memory (transposed + padded so that a
-//                      warp's 32 words read 32 different banks), one warp per row, 16 codes per lane per load,
-//                      the weight picked from wtab by code and multiplied into every token's accumulator
-//   tl_expand_kernel   codes -> dense Wq (f32/f16/bf16) or T (int8) in ORIGINAL column positions, for the
+//   tl_gemv_kernel     <= 4 tokens per launch, by table lookup: per chunk of positions the CTA first builds, in shared
+//                      memory, the 16 subset sums of every group of 4 gathered inputs; a weight row then costs two
+//                      lookups per group (the +1 nibble and the -1 nibble) instead of 4 multiply-adds:
+//                          y += w0 * sum(x) + (w+ - w0) * sum_{T=+1} x + (w- - w0) * sum_{T=-1} x      per code word
+//                      (the differences are formed in fp32 from the rounded weights).  One warp per row, one code word
+//                      per lane per step; the table columns are rotated so the 32 lanes of a lookup hit 32 banks.
+//   tl_expand_kernel   codes -> dense Wq (f32/f16/bf16) or T (int8) in ORIGINAL column positions, for fp32 layers'
 //                      many-token path (library GEMM on the dense weight) and for reading T back
 #include "common.cuh"
 
 namespace tq {
 
-constexpr int TL_KW = 128;            // words of one row staged per chunk (2048 positions)
-constexpr int TL_ROWS_PER_WARP = 2;
-constexpr int TL_WARPS = 8;
+constexpr int TL_THREADS = 1024;          // gemv CTA: 32 warps = 32 rows
+constexpr int TL_ENTRIES = 4096;          // floats of lookup table per nibble value set: positions per chunk * tokens = 4096
 
 __global__ void __launch_bounds__(256)
 tl_pack_kernel(const int8_t* __restrict__ Torig, int64_t n, int64_t m, const int32_t* __restrict__ perm,
@@ -40,9 +43,11 @@ tl_pack_kernel(const int8_t* __restrict__ Torig, int64_t n, int64_t m, const int
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             const int64_t p = w * 16 + j;
-            uint32_t c = 1u;
-            if (p < m) c = (uint32_t)((int)row[perm ? perm[p] : p] + 1) & 3u;
-            word |= c << (2 * j);
+            if (p < m) {
+                const int t = row[perm ? perm[p] : p];
+                word |= (t > 0 ? 1u : 0u) << j;
+                word |= (t < 0 ? 1u : 0u) << (16 + j);
+            }
         }
         codes[q] = word;
     }
@@ -67,89 +72,131 @@ tl_wtab_kernel(const float* __restrict__ alpha, const float* __restrict__ mu, in
     }
 }
 
-__device__ __forceinline__ float tl_pick(const float4& wt, uint32_t c) {
-    return c == 0u ? wt.x : (c == 1u ? wt.y : wt.z);
+// weight of position j of a code word
+__device__ __forceinline__ float tl_pick(const float4& wt, uint32_t word, int j) {
+    return ((word >> j) & 1u) ? wt.z : (((word >> (16 + j)) & 1u) ? wt.x : wt.y);
 }
 
-// xs layout: [16][TL_KW + 1][MT] floats; position (j, wl) = chunk position 16*wl + j.  A warp reads (j, lane + 32 i)
-// for fixed j: consecutive lanes are MT floats apart -> conflict-free vector loads.
+// Lookup table of one chunk: KC = TL_ENTRIES / MT positions = KC/4 groups of 4 positions; 128 groups (512 positions,
+// the 32 code words one warp step reads) form a segment.  Entry (segment s, nibble v, group gl of the segment, token t)
+// lives at  tab[((s * 16 + v) * 128 + col(gl)) * MT + t],  col(gl) = (gl & ~31) | ((gl + (gl >> 5)) & 31):
+// lane l looks up groups 4l + i, i.e. columns 32a + ((4b + i + a) & 31) with l = 8a + b -- 32 distinct banks.
+__device__ __forceinline__ int tl_col(int gl) { return (gl & ~31) | ((gl + (gl >> 5)) & 31); }
+
+template <int MT> struct TlVec;
+template <> struct TlVec<1> { using type = float; };
+template <> struct TlVec<2> { using type = float2; };
+template <> struct TlVec<4> { using type = float4; };
+
+template <int MT>
+__device__ __forceinline__ void tl_lookup_add(const float* tab, int index, float (&acc)[MT]) {
+    const typename TlVec<MT>::type v = *reinterpret_cast<const typename TlVec<MT>::type*>(tab + (size_t)index * MT);
+    if constexpr (MT == 1) { acc[0] += v; }
+    else if constexpr (MT == 2) { acc[0] += v.x; acc[1] += v.y; }
+    else { acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w; }
+}
+
 template <typename XT, int MT>
-__global__ void __launch_bounds__(TL_WARPS * 32)
+__global__ void __launch_bounds__(TL_THREADS, 1)
 tl_gemv_kernel(const uint32_t* __restrict__ codes, int64_t wpr, const float4* __restrict__ wtab, int n, int m, int nb,
-               int block, const XT* __restrict__ x, int64_t ldx, int M, const int32_t* __restrict__ perm,
+               int wpb, int wpb_shift, const XT* __restrict__ x, int64_t ldx, int M, const int32_t* __restrict__ perm,
                const float* __restrict__ bias, float* __restrict__ y, int64_t ldy) {
-    __shared__ __align__(16) float xs[16 * (TL_KW + 1) * MT];
+    constexpr int KC = TL_ENTRIES / MT;          // positions per chunk
+    constexpr int GPC = KC / 4;                  // groups per chunk (= threads per token in the build phase)
+    constexpr int SEGS = KC / 512;               // warp steps per chunk
+    extern __shared__ __align__(16) float tl_smem[];
+    float* tab = tl_smem;                        // [SEGS][16][128][MT]
+    float* wsum = tl_smem + (size_t)SEGS * 16 * 128 * MT;      // [KC/16][MT] sum of the 16 inputs of each code word
+
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int row0 = (blockIdx.x * TL_WARPS + warp) * TL_ROWS_PER_WARP;
-    const int words = (m + 15) >> 4;                         // words of a row that hold real positions
+    const int r = blockIdx.x * 32 + warp;
+    const bool live = r < n;
+    const int words = (m + 15) >> 4;
+    const uint32_t* crow = codes + (int64_t)(live ? r : 0) * wpr;
+    const float4* trow = wtab + (int64_t)(live ? r : 0) * nb;
 
-    float acc[TL_ROWS_PER_WARP][MT];
+    int colbase[4];                              // table column of this lane's i-th group within a segment
 #pragma unroll
-    for (int i = 0; i < TL_ROWS_PER_WARP; ++i)
-#pragma unroll
-        for (int t = 0; t < MT; ++t) acc[i][t] = 0.f;
+    for (int i = 0; i < 4; ++i) colbase[i] = tl_col(4 * lane + i);
 
-    for (int c0 = 0; c0 < m; c0 += TL_KW * 16) {
-        const int w0 = c0 >> 4;
-        // the chunk's code words first (independent global loads in flight while x is staged)
-        uint32_t wd[TL_ROWS_PER_WARP][TL_KW / 32];
+    // build-phase role: (token bt, group bg of the chunk)
+    const int bt = threadIdx.x / GPC, bg = threadIdx.x - bt * GPC;
+
+    float acc[MT];
 #pragma unroll
-        for (int i = 0; i < TL_ROWS_PER_WARP; ++i)
+    for (int t = 0; t < MT; ++t) acc[t] = 0.f;
+
+    for (int c0 = 0; c0 < m; c0 += KC) {
+        // this chunk's code words first: independent global loads in flight while the table is built
+        uint32_t wd[SEGS];
 #pragma unroll
-            for (int s = 0; s < TL_KW / 32; ++s) {
-                const int w = w0 + lane + 32 * s;
-                const int r = row0 + i;
-                wd[i][s] = (r < n && w < words) ? __ldg(codes + (int64_t)r * wpr + w) : 0x55555555u;
+        for (int s = 0; s < SEGS; ++s) {
+            const int w = (c0 >> 4) + 32 * s + lane;
+            wd[s] = (live && w < words) ? __ldg(crow + w) : 0u;
+        }
+        __syncthreads();                         // previous chunk's table fully consumed
+        {
+            // the 16 subset sums of inputs 4 bg .. 4 bg + 3 of token bt (entry v = sum of x_j over the bits j of v)
+            float xv[4];
+            const int p0 = c0 + 4 * bg;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int p = p0 + j;
+                float v = 0.f;
+                if (p < m && bt < M) v = to_f32<XT>(x[(int64_t)bt * ldx + (perm ? perm[p] : p)]);
+                xv[j] = v;
             }
-        __syncthreads();                                     // previous chunk fully consumed
-        for (int idx = threadIdx.x; idx < TL_KW * 16; idx += TL_WARPS * 32) {
-            const int p = c0 + idx;
-            const int col = p < m ? (perm ? perm[p] : p) : -1;
-            float* dst = xs + ((idx & 15) * (TL_KW + 1) + (idx >> 4)) * MT;
+            float e[16];
+            e[0] = 0.f;
 #pragma unroll
-            for (int t = 0; t < MT; ++t) dst[t] = (col >= 0 && t < M) ? to_f32<XT>(x[(int64_t)t * ldx + col]) : 0.f;
+            for (int v = 1; v < 16; ++v) {
+                const int low = v & (-v);                                  // lowest set bit
+                const int j = (low == 1) ? 0 : (low == 2) ? 1 : (low == 4) ? 2 : 3;
+                e[v] = e[v ^ low] + xv[j];
+            }
+            const int seg = bg >> 7, col = tl_col(bg & 127);
+            float* dst = tab + ((size_t)(seg * 16) * 128 + col) * MT + bt;
+#pragma unroll
+            for (int v = 0; v < 16; ++v) dst[(size_t)v * 128 * MT] = e[v];
+            // word totals: groups 4q .. 4q+3 are adjacent lanes
+            float tot = e[15];
+            tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+            tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+            if ((bg & 3) == 0) wsum[(bg >> 2) * MT + bt] = tot;
         }
         __syncthreads();
+        if (live) {
 #pragma unroll
-        for (int s = 0; s < TL_KW / 32; ++s) {
-            const int wl = lane + 32 * s;
-            const int w = w0 + wl;
-            if (w >= words) continue;
-            const int k = min((w * 16) / block, nb - 1);
-            float4 wt[TL_ROWS_PER_WARP];
+            for (int s = 0; s < SEGS; ++s) {
+                const int wl = 32 * s + lane;                              // word within the chunk
+                const int w = (c0 >> 4) + wl;
+                if (w >= words) continue;
+                const uint32_t word = wd[s];
+                const float* seg = tab + (size_t)s * 16 * 128 * MT;
+                float sp[MT], sn[MT];
 #pragma unroll
-            for (int i = 0; i < TL_ROWS_PER_WARP; ++i)
-                wt[i] = (row0 + i < n) ? __ldg(wtab + (int64_t)(row0 + i) * nb + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int t = 0; t < MT; ++t) { sp[t] = 0.f; sn[t] = 0.f; }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                float xv[MT];
-                const float* src = xs + (j * (TL_KW + 1) + wl) * MT;
-                if constexpr (MT == 4) {
-                    const float4 v = *reinterpret_cast<const float4*>(src);
-                    xv[0] = v.x; xv[1] = v.y; xv[2] = v.z; xv[3] = v.w;
-                } else if constexpr (MT == 2) {
-                    const float2 v = *reinterpret_cast<const float2*>(src);
-                    xv[0] = v.x; xv[1] = v.y;
-                } else {
-                    xv[0] = src[0];
+                for (int i = 0; i < 4; ++i) {
+                    tl_lookup_add<MT>(seg, (int)((word >> (4 * i)) & 15u) * 128 + colbase[i], sp);
+                    tl_lookup_add<MT>(seg, (int)((word >> (16 + 4 * i)) & 15u) * 128 + colbase[i], sn);
                 }
+                const int k = wpb_shift >= 0 ? (w >> wpb_shift) : (w / wpb);      // code words per block: usually 8
+                const float4 wt = __ldg(trow + min(k, nb - 1));
+                const float dp = __fsub_rn(wt.z, wt.y), dn = __fsub_rn(wt.x, wt.y);
 #pragma unroll
-                for (int i = 0; i < TL_ROWS_PER_WARP; ++i) {
-                    const float wv = tl_pick(wt[i], (wd[i][s] >> (2 * j)) & 3u);
-#pragma unroll
-                    for (int t = 0; t < MT; ++t) acc[i][t] = fmaf(wv, xv[t], acc[i][t]);
+                for (int t = 0; t < MT; ++t) {
+                    const float tot = wsum[wl * MT + t];
+                    acc[t] = fmaf(wt.y, tot, fmaf(dp, sp[t], fmaf(dn, sn[t], acc[t])));
                 }
             }
         }
     }
 #pragma unroll
-    for (int i = 0; i < TL_ROWS_PER_WARP; ++i)
-#pragma unroll
-        for (int t = 0; t < MT; ++t) {
-            const float v = warp_sum(acc[i][t]);
-            const int r = row0 + i;
-            if (lane == 0 && r < n && t < M) y[(int64_t)t * ldy + r] = bias ? __fadd_rn(v, bias[r]) : v;
-        }
+    for (int t = 0; t < MT; ++t) {
+        const float v = warp_sum(acc[t]);
+        if (lane == 0 && live && t < M) y[(int64_t)t * ldy + r] = bias ? __fadd_rn(v, bias[r]) : v;
+    }
 }
 
 template <typename OT> __device__ __forceinline__ OT tl_cast(float v);
@@ -158,26 +205,47 @@ template <> __device__ __forceinline__ __half tl_cast<__half>(float v) { return 
 template <> __device__ __forceinline__ __nv_bfloat16 tl_cast<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 template <> __device__ __forceinline__ int8_t tl_cast<int8_t>(float v) { return (int8_t)v; }
 
-// one thread per code word; wtab == nullptr expands to T = code - 1
+// one thread per PAIR of positions, consecutive threads = consecutive pairs of one row (grid.y strides over rows): with the
+// identity order a warp writes 64 consecutive elements; wtab == nullptr expands to T
 template <typename OT>
 __global__ void __launch_bounds__(256)
-tl_expand_kernel(const uint32_t* __restrict__ codes, int64_t wpr, const float4* __restrict__ wtab, int64_t n, int64_t m,
-                 int64_t nb, int64_t block, const int32_t* __restrict__ perm, OT* __restrict__ out, int64_t ldo) {
-    const int64_t words = (m + 15) >> 4;
-    const int64_t total = n * words;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = q / words, w = q - r * words;
-        const uint32_t word = codes[r * wpr + w];
-        int64_t k = (w * 16) / block;
-        if (k > nb - 1) k = nb - 1;
-        const float4 wt = wtab ? wtab[r * nb + k] : make_float4(-1.f, 0.f, 1.f, 0.f);
-        OT* row = out + r * ldo;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int64_t p = w * 16 + j;
-            if (p < m) row[perm ? perm[p] : p] = tl_cast<OT>(tl_pick(wt, (word >> (2 * j)) & 3u));
+tl_expand_kernel(const uint32_t* __restrict__ codes, int64_t wpr, const float4* __restrict__ wtab, int n, int m, int nb,
+                 int wpb, int wpb_shift, const int32_t* __restrict__ perm, OT* __restrict__ out, int64_t ldo) {
+    const int pairs = (m + 1) >> 1;
+    for (int r = blockIdx.y; r < n; r += gridDim.y) {
+        const uint32_t* crow = codes + (int64_t)r * wpr;
+        OT* row = out + (int64_t)r * ldo;
+        for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < pairs; q += gridDim.x * blockDim.x) {
+            const int p0 = q * 2;
+            const int w = p0 >> 4, j = p0 & 15;
+            const uint32_t word = __ldg(crow + w);
+            const int k = min(wpb_shift >= 0 ? (w >> wpb_shift) : (w / wpb), nb - 1);
+            const float4 wt = wtab ? __ldg(wtab + (int64_t)r * nb + k) : make_float4(-1.f, 0.f, 1.f, 0.f);
+            const OT v0 = tl_cast<OT>(tl_pick(wt, word, j));
+            const OT v1 = tl_cast<OT>(tl_pick(wt, word, j + 1));
+            if (perm) {
+                row[perm[p0]] = v0;
+                if (p0 + 1 < m) row[perm[p0 + 1]] = v1;
+            } else {
+                row[p0] = v0;
+                if (p0 + 1 < m) row[p0 + 1] = v1;
+            }
         }
     }
+}
+
+template <typename OT>
+static int launch_expand(const uint32_t* codes, int64_t wpr, const float4* wt, int64_t n, int64_t m, int64_t nb, int64_t block,
+                         const int32_t* perm, OT* out, int64_t ldo, cudaStream_t st) {
+    const int wpb = (int)(block / 16) > 0 ? (int)(block / 16) : 1;
+    int wpb_shift = -1;
+    for (int sft = 0; sft < 28; ++sft)
+        if ((1 << sft) == wpb) wpb_shift = sft;
+    const int64_t pairs = (m + 1) / 2;
+    dim3 grid((unsigned)(ceil_div(pairs, 256) < 32 ? ceil_div(pairs, 256) : 32), (unsigned)(n < 65535 ? n : 65535));
+    tl_expand_kernel<OT><<<grid, 256, 0, st>>>(codes, wpr, wt, (int)n, (int)m, (int)nb, wpb, wpb_shift, perm, out, ldo);
+    TQ_LAUNCH_CHECK("tl_expand_kernel");
+    return 0;
 }
 
 static inline unsigned tl_grid(int64_t work, int threads) {
@@ -188,26 +256,42 @@ static inline unsigned tl_grid(int64_t work, int threads) {
     return (unsigned)g;
 }
 
+template <int MT> constexpr int tl_gemv_smem() { return (TL_ENTRIES / MT / 512) * 16 * 128 * MT * 4 + (TL_ENTRIES / MT / 16) * MT * 4; }
+
+template <typename XT, int MT>
+static int launch_gemv_mt(const uint32_t* codes, int64_t wpr, const float4* wt, int64_t n, int64_t m, int64_t nb,
+                          int64_t block, const XT* x, int64_t ldx, int mt, const int32_t* perm, const float* bias, float* y,
+                          int64_t ldy, cudaStream_t st) {
+    constexpr int smem = tl_gemv_smem<MT>();
+    static bool attr_set = false;
+    if (!attr_set) {
+        TQ_CUDA(cudaFuncSetAttribute(tl_gemv_kernel<XT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    const int wpb = (int)(block / 16);
+    int wpb_shift = -1;
+    for (int sft = 0; sft < 20; ++sft)
+        if ((1 << sft) == wpb) wpb_shift = sft;
+    tl_gemv_kernel<XT, MT><<<(unsigned)ceil_div(n, 32), TL_THREADS, smem, st>>>(codes, wpr, wt, (int)n, (int)m, (int)nb, wpb,
+                                                                               wpb_shift, x, ldx, mt, perm, bias, y, ldy);
+    TQ_LAUNCH_CHECK("tl_gemv_kernel");
+    return 0;
+}
+
 template <typename XT>
 static int launch_gemv(const uint32_t* codes, int64_t wpr, const float* wtab, int64_t n, int64_t m, int64_t nb,
                        int64_t block, const XT* x, int64_t ldx, int64_t M, const int32_t* perm, const float* bias,
                        float* y, int64_t ldy, cudaStream_t st) {
-    const unsigned grid = (unsigned)ceil_div(n, TL_WARPS * TL_ROWS_PER_WARP);
     const float4* wt = reinterpret_cast<const float4*>(wtab);
     for (int64_t t0 = 0; t0 < M; t0 += 4) {
         const int mt = (int)((M - t0) < 4 ? (M - t0) : 4);
         const XT* xt = x + t0 * ldx;
         float* yt = y + t0 * ldy;
-        if (mt == 1)
-            tl_gemv_kernel<XT, 1><<<grid, TL_WARPS * 32, 0, st>>>(codes, wpr, wt, (int)n, (int)m, (int)nb, (int)block, xt,
-                                                                  ldx, mt, perm, bias, yt, ldy);
-        else if (mt == 2)
-            tl_gemv_kernel<XT, 2><<<grid, TL_WARPS * 32, 0, st>>>(codes, wpr, wt, (int)n, (int)m, (int)nb, (int)block, xt,
-                                                                  ldx, mt, perm, bias, yt, ldy);
-        else
-            tl_gemv_kernel<XT, 4><<<grid, TL_WARPS * 32, 0, st>>>(codes, wpr, wt, (int)n, (int)m, (int)nb, (int)block, xt,
-                                                                  ldx, mt, perm, bias, yt, ldy);
-        TQ_LAUNCH_CHECK("tl_gemv_kernel");
+        int rc;
+        if (mt == 1) rc = launch_gemv_mt<XT, 1>(codes, wpr, wt, n, m, nb, block, xt, ldx, mt, perm, bias, yt, ldy, st);
+        else if (mt == 2) rc = launch_gemv_mt<XT, 2>(codes, wpr, wt, n, m, nb, block, xt, ldx, mt, perm, bias, yt, ldy, st);
+        else rc = launch_gemv_mt<XT, 4>(codes, wpr, wt, n, m, nb, block, xt, ldx, mt, perm, bias, yt, ldy, st);
+        if (rc) return rc;
     }
     return 0;
 }
@@ -248,7 +332,7 @@ extern "C" int tq_tl_gemv(const uint32_t* codes, int64_t wpr, const float* wtab,
     using namespace tq;
     TQ_CHECK_ARG(codes && wtab && x && y && n > 0 && m > 0 && M >= 0 && wpr >= ceil_div(m, 16) && ldx >= m && ldy >= n,
                  "tq_tl_gemv: bad arguments");
-    TQ_CHECK_ARG(n < (1ll << 31) && m < (1ll << 31), "tq_tl_gemv: shape too large");
+    TQ_CHECK_ARG(n < (1ll << 31) - 64 && m < (1ll << 31) - 8192, "tq_tl_gemv: shape too large");
     if (block <= 0 || block % 16 != 0) {
         set_error("tq_tl_gemv: block size %lld is not a positive multiple of 16 (a code word must not straddle blocks)",
                   (long long)block);
@@ -275,24 +359,21 @@ extern "C" int tq_tl_dequant(const uint32_t* codes, int64_t wpr, const float* wt
         return TQ_E_UNSUPPORTED;
     }
     TQ_CHECK_ARG((reinterpret_cast<uintptr_t>(wtab) & 15) == 0, "tq_tl_dequant: wtab must be 16-byte aligned");
+    TQ_CHECK_ARG(n < (1ll << 31) && m < (1ll << 31) - 2, "tq_tl_dequant: shape too large");
     const int64_t nb = ceil_div(m, block);
     cudaStream_t st = (cudaStream_t)stream;
     const float4* wt = reinterpret_cast<const float4*>(wtab);
-    const unsigned grid = tl_grid(n * ceil_div(m, 16), 256);
-    if (wdtype == TQ_F32) tl_expand_kernel<float><<<grid, 256, 0, st>>>(codes, wpr, wt, n, m, nb, block, perm, (float*)W, ldw);
-    else if (wdtype == TQ_F16) tl_expand_kernel<__half><<<grid, 256, 0, st>>>(codes, wpr, wt, n, m, nb, block, perm, (__half*)W, ldw);
-    else if (wdtype == TQ_BF16) tl_expand_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(codes, wpr, wt, n, m, nb, block, perm, (__nv_bfloat16*)W, ldw);
-    else { set_error("tq_tl_dequant: unknown dtype %d", wdtype); return TQ_E_BADARG; }
-    TQ_LAUNCH_CHECK("tl_expand_kernel");
-    return 0;
+    if (wdtype == TQ_F32) return launch_expand<float>(codes, wpr, wt, n, m, nb, block, perm, (float*)W, ldw, st);
+    if (wdtype == TQ_F16) return launch_expand<__half>(codes, wpr, wt, n, m, nb, block, perm, (__half*)W, ldw, st);
+    if (wdtype == TQ_BF16) return launch_expand<__nv_bfloat16>(codes, wpr, wt, n, m, nb, block, perm, (__nv_bfloat16*)W, ldw, st);
+    set_error("tq_tl_dequant: unknown dtype %d", wdtype);
+    return TQ_E_BADARG;
 }
 
 extern "C" int tq_tl_unpack(const uint32_t* codes, int64_t wpr, int64_t n, int64_t m, const int32_t* perm, int8_t* Torig,
                             void* stream) {
     using namespace tq;
     TQ_CHECK_ARG(codes && Torig && n > 0 && m > 0 && wpr >= ceil_div(m, 16), "tq_tl_unpack: bad arguments");
-    tl_expand_kernel<int8_t><<<tl_grid(n * ceil_div(m, 16), 256), 256, 0, (cudaStream_t)stream>>>(
-        codes, wpr, nullptr, n, m, 1, m, perm, Torig, m);
-    TQ_LAUNCH_CHECK("tl_expand_kernel<int8>");
-    return 0;
+    TQ_CHECK_ARG(n < (1ll << 31) && m < (1ll << 31) - 2, "tq_tl_unpack: shape too large");
+    return launch_expand<int8_t>(codes, wpr, nullptr, n, m, 1, ((m + 15) / 16) * 16, perm, Torig, m, (cudaStream_t)stream);
 }

@@ -6,7 +6,8 @@
 ``TernaryLinear`` keeps the reference's constructor, ``set_quantized_params(alpha, mu, T, perm, bias)``,
 ``forward``, ``_dequantize`` and ``memory_footprint``, but
 
-  * stores the codes as 2 bits per weight in sweep order (``codes``, the TL2 layout of include/tq100.h) instead of
+  * stores the codes as 2 bits per weight (a +1 and a -1 bit plane per 16 positions) in sweep order (``codes``, the TL2
+    layout of include/tq100.h) instead of
     an int8 matrix (1 byte per weight, model.py:43); ``T`` is a read-only property that unpacks them;
   * computes ``F.linear(x, Wq)`` with ``Wq = GPTQ.get_quantized_weight()`` (gptq.py:201-230).  The reference's
     forward (model.py:84-90) gathers the input by ``perm`` AND un-permutes a weight whose T is already stored in
@@ -52,8 +53,8 @@ class TernaryLinear(nn.Module):
         self.block_size = block_size
         num_blocks = (in_features + block_size - 1) // block_size
         wpr = (in_features + 15) // 16
-        # code 1 = T 0 everywhere (0x55555555), like the reference's zero-initialised T (model.py:43)
-        self.register_buffer("codes", torch.full((out_features, wpr), 0x55555555, dtype=torch.int32, device=device))
+        # both bit planes empty = T 0 everywhere, like the reference's zero-initialised T (model.py:43)
+        self.register_buffer("codes", torch.zeros((out_features, wpr), dtype=torch.int32, device=device))
         self.register_buffer("alpha", torch.ones(out_features, num_blocks, dtype=dtype, device=device))
         self.register_buffer("mu", torch.zeros(out_features, num_blocks, dtype=dtype, device=device))
         self.register_buffer("perm", torch.arange(in_features, dtype=torch.long, device=device))

@@ -54,7 +54,8 @@ def _wtab(G, alpha, mu, dtype):
     L = G.lib()
     n, nb = alpha.shape
     wtab = torch.empty((n, nb, 4), dtype=torch.float32, device=G.DEV)
-    _lib.check(L.tq_tl_wtab(_lib.ptr(G.dev(alpha)), _lib.ptr(G.dev(mu)), n, nb, _lib.dtype_code(TDT[dtype]),
+    a, u = G.dev(alpha), G.dev(mu)          # named: a temporary would be freed (and its block reused) before the launch
+    _lib.check(L.tq_tl_wtab(_lib.ptr(a), _lib.ptr(u), n, nb, _lib.dtype_code(TDT[dtype]),
                             _lib.ptr(wtab), _lib.stream()), "tq_tl_wtab")
     torch.cuda.synchronize()
     return wtab
@@ -94,7 +95,7 @@ def test_tl_wtab_and_dequant_bit_exact(G, dtype):
 
 @pytest.mark.parametrize("xdtype", ["float32", "float16", "bfloat16"])
 @pytest.mark.parametrize("n,m,block,identity", [(48, 320, 128, False), (33, 2500, 64, False), (130, 4224, 128, True),
-                                                 (17, 100, 128, False)])
+                                                 (17, 100, 128, False), (70, 11008, 128, False)])
 def test_tl_gemv_vs_oracle(G, n, m, block, identity, xdtype):
     from tq100 import _lib
     L = G.lib()
@@ -110,9 +111,11 @@ def test_tl_gemv_vs_oracle(G, n, m, block, identity, xdtype):
         xr = x.float().cpu().numpy().astype(np.float64)
         for b in (None, bias):
             y = torch.full((M, n), float("nan"), dtype=torch.float32, device=G.DEV)
+            bd = None if b is None else G.dev(b)
             _lib.check(L.tq_tl_gemv(_lib.ptr(codes), codes.shape[1], _lib.ptr(wtab), n, m, block, _lib.ptr(x),
-                                    _lib.dtype_code(x.dtype), m, M, _lib.ptr(pd), _lib.ptr(None if b is None else G.dev(b)),
+                                    _lib.dtype_code(x.dtype), m, M, _lib.ptr(pd), _lib.ptr(bd),
                                     _lib.ptr(y), n, _lib.stream()), "tq_tl_gemv")
+            torch.cuda.synchronize()
             want = otl.forward(xr, alpha, mu, T, perm, b, block, wdtype)
             bound = 1e-5 * (np.abs(xr) @ np.abs(Wq).T + (0 if b is None else np.abs(b))) + 1e-12
             got = y.cpu().numpy().astype(np.float64)

@@ -67,7 +67,7 @@ def test_ssr_permutation_reference_forward_is_not_the_quantised_layer():
     assert np.abs(ref - want).max() > 0.05 * np.abs(want).max()
 
 
-def test_pack_layer_roundtrip_and_flat_codec_agreement():
+def test_pack_layer_roundtrip_and_planes():
     rng = np.random.default_rng(7)
     for n, m in ((5, 16), (3, 37), (9, 320), (4, 128)):
         T = rng.integers(-1, 2, size=(n, m)).astype(np.int8)
@@ -75,13 +75,13 @@ def test_pack_layer_roundtrip_and_flat_codec_agreement():
         words = otl.pack_layer(T, perm)
         assert words.shape == (n, (m + 15) // 16) and words.dtype == np.uint32
         assert np.array_equal(otl.unpack_layer(words, m, perm), T)
-        if m % 16:       # padding positions carry code 1 (T = 0)
-            tail = words[:, -1] >> np.uint32(2 * (m % 16))
-            assert np.all(tail == (0x55555555 >> (2 * (m % 16))))
-        if m % 16 == 0:  # identity order: the words are the reference's flat byte stream (utils.py:189-219)
-            ident = otl.pack_layer(T, np.arange(m))
-            flat, _ = oracle.pack_ternary(T)
-            assert np.array_equal(ident.view(np.uint8).reshape(-1), flat)
+        assert not np.any(words & (words >> np.uint32(16)) & np.uint32(0xFFFF))     # a position is never both +1 and -1
+        if m % 16:       # padding positions are T = 0 in both planes
+            keep = np.uint32((1 << (m % 16)) - 1)
+            assert np.all((words[:, -1] & np.uint32(0xFFFF) & ~keep) == 0)
+            assert np.all(((words[:, -1] >> np.uint32(16)) & ~keep) == 0)
+    T = np.array([[1, -1, 0, 1] + [0] * 12], dtype=np.int8)
+    assert otl.pack_layer(T, np.arange(16))[0, 0] == (0b1001 | (0b0010 << 16))
 
 
 def test_weight_table_values():
