@@ -202,7 +202,9 @@ int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const float* Hd,
  *                  dtype wtab was built for), fp32 accumulation; needs m % 8 == 0 and 16-byte aligned x; xperm_work
  *                  [M, m] of xdtype is the gather buffer for x[:, perm] (model.py:84), unused when perm is NULL
  *   tq_tl_dequant  dense Wq [n, ldw] of wdtype in ORIGINAL column positions (model.py:97-110 / gptq.py:201-230)
- *   tq_tl_unpack   T int8 [n, m] in original positions */
+ *   tq_tl_unpack   T int8 [n, m] in original positions
+ * tq_tl_dequant / tq_tl_unpack: inv_perm (int32 [m], inv_perm[perm[p]] = p) is optional; with it the kernels gather
+ * codes and write coalesced rows, without it a permuted layer is scattered column by column. */
 int64_t tq_tl_words_per_row(int64_t m);
 int tq_tl_pack(const int8_t* Torig, int64_t n, int64_t m, const int32_t* perm, uint32_t* codes, int64_t wpr,
                void* stream);
@@ -214,9 +216,9 @@ int tq_tl_gemm_tc(const uint32_t* codes, int64_t wpr, const float* wtab, int64_t
                   const void* x, int xdtype, int64_t ldx, int64_t M, const int32_t* perm, void* xperm_work,
                   const float* bias, void* y, int64_t ldy, void* stream);
 int tq_tl_dequant(const uint32_t* codes, int64_t wpr, const float* wtab, int64_t n, int64_t m, int64_t block,
-                  const int32_t* perm, void* W, int wdtype, int64_t ldw, void* stream);
-int tq_tl_unpack(const uint32_t* codes, int64_t wpr, int64_t n, int64_t m, const int32_t* perm, int8_t* Torig,
-                 void* stream);
+                  const int32_t* perm, const int32_t* inv_perm, void* W, int wdtype, int64_t ldw, void* stream);
+int tq_tl_unpack(const uint32_t* codes, int64_t wpr, int64_t n, int64_t m, const int32_t* perm,
+                 const int32_t* inv_perm, int8_t* Torig, void* stream);
 
 /* ---- communicator for the row-sharded sweep ------------------------------------------
  * One process per GPU.  Rank 0 calls tq_comm_unique_id (128 bytes, host), ships the bytes to the other

@@ -58,8 +58,8 @@ _SIGNATURES = {
     "tq_tl_wtab": (_int, [_ptr, _ptr, _i64, _i64, _int, _ptr, _ptr]),
     "tq_tl_gemv": (_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _int, _i64, _i64, _ptr, _ptr, _ptr, _i64, _ptr]),
     "tq_tl_gemm_tc": (_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _int, _i64, _i64, _ptr, _ptr, _ptr, _ptr, _i64, _ptr]),
-    "tq_tl_dequant": (_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _ptr, _int, _i64, _ptr]),
-    "tq_tl_unpack": (_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr]),
+    "tq_tl_dequant": (_int, [_ptr, _i64, _ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _int, _i64, _ptr]),
+    "tq_tl_unpack": (_int, [_ptr, _i64, _i64, _i64, _ptr, _ptr, _ptr, _ptr]),
     "tq_comm_unique_id": (_int, [_ptr]),
     "tq_comm_init": (_int, [_ptr, _int, _int]),
     "tq_comm_ready": (_int, []),

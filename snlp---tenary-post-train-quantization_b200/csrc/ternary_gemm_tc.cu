@@ -4,7 +4,7 @@
 //
 //   D[128 weight rows, 256 tokens] (fp32, TMEM) += A[128 x 64] * B[256 x 64]',  kind::f16, UMMA 128x256x16
 //   (128-token tiles, UMMA 128x128x16, when 256-token tiles would leave SMs without work)
-//   A = dequantised weights, K-major, 128B-swizzled, WRITTEN BY EIGHT DEQUANT WARPS from the TL2 code words
+//   A = dequantised weights, K-major, 128B-swizzled, WRITTEN BY SIXTEEN DEQUANT WARPS from the TL2 code words
 //       (ternary_linear.cu): value = wtab[row, p/block][code], already rounded to the layer's 16-bit dtype, so the
 //       tensor core multiplies exactly the reference's fp16/bf16 weight `alpha * T + mu`;
 //   B = activations [tokens, m] in sweep order (gathered by perm beforehand when perm is not the identity,
@@ -14,7 +14,8 @@
 //   TMEM: 2 accumulators x 256 columns, so the epilogue of one tile overlaps the MMAs of the next;
 //   epilogue: tcgen05.ld -> (+ bias) -> 16-bit stores y[token, row] with lanes along the rows (contiguous in y);
 //   schedule: persistent CTAs; tiles ordered token-tile-major so concurrently running CTAs share the same x slab in L2.
-//   roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue, warps 8-15 dequant.
+//   roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue, warps 8-23 dequant
+//   (sixteen warps: the expansion is ~5 integer instructions per weight and needs the issue slots of all four schedulers).
 #include "tc_common.cuh"
 
 namespace tq {
@@ -22,8 +23,8 @@ namespace tq {
 constexpr int TG_BM = 128, TG_BK = 64, TG_STAGES = 4, TG_UMMA_K = 16;
 constexpr int TG_A_BYTES = TG_BM * TG_BK * 2;                 // 16384
 constexpr int TG_STAGE_BYTES = TG_A_BYTES + 256 * TG_BK * 2;  // 49152: A + the widest B tile (256 tokens)
-constexpr int TG_THREADS = 512;
-constexpr int TG_DEQ_THREADS = 256;
+constexpr int TG_THREADS = 768;
+constexpr int TG_DEQ_THREADS = 512;
 constexpr int TG_DEQ_WARPS = TG_DEQ_THREADS / 32;
 constexpr int TG_SMEM = TG_STAGES * TG_STAGE_BYTES + 256 + 1024;
 
@@ -32,7 +33,8 @@ struct TgProblem {
     int64_t wpr;
     const float4* wtab;
     int n, m, nb, block, M;
-    int wpb, wpb_shift;              // code words per scale block (block / 16); its log2 when a power of two, else -1
+    int wpb_shift;                   // log2 of the code words per scale block (block / 16) when a power of two, else -1
+    uint32_t wpb_magic;              // ceil(2^32 / (block / 16)): multiply-high division otherwise
     int row_tiles, tok_tiles, ksteps;
     const float* bias;
     void* y;
@@ -162,11 +164,11 @@ tl_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TgProblem p, 
             }
         }
     } else if (warp >= 8) {
-        // ===== dequant producers: thread = (row of the tile, half of the 64-wide K slab = 2 code words) =====
-        // Code words and their weight-table entries are fetched TWO slabs ahead of the one being expanded: with one
+        // ===== dequant producers: thread = (row of the tile, quarter of the 64-wide K slab = 1 code word) =====
+        // The code word and its weight-table entry are fetched TWO slabs ahead of the one being expanded: with one
         // CTA per SM nothing else hides the L2 latency of these loads.
         const int dt = threadIdx.x - 256;
-        const int row = dt >> 1, h = dt & 1;
+        const int row = dt >> 2, h = dt & 3;
         const int words = (p.m + 15) >> 4;
         int stage = 0, phase = 0;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
@@ -176,42 +178,37 @@ tl_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TgProblem p, 
             const uint32_t* crow = p.codes + (int64_t)(live ? r : 0) * p.wpr;
             const float4* trow = p.wtab + (int64_t)(live ? r : 0) * p.nb;
             const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            auto blk_of = [&](int w) { return p.wpb_shift >= 0 ? (w >> p.wpb_shift) : (w / p.wpb); };
-            auto fetch = [&](int ks, uint32_t& a, uint32_t& b, float4& ta, float4& tb) {
-                const int w = ks * 4 + 2 * h;
-                a = 0u; b = 0u; ta = zero4; tb = zero4;            // out of range: zeros in both planes AND a zero table
-                if (live && ks < p.ksteps) {
-                    if (w < words) { a = __ldg(crow + w); ta = __ldg(trow + min(blk_of(w), p.nb - 1)); }
-                    if (w + 1 < words) { b = __ldg(crow + w + 1); tb = __ldg(trow + min(blk_of(w + 1), p.nb - 1)); }
+            auto fetch = [&](int ks, uint32_t& a, float4& ta) {
+                const int w = ks * 4 + h;
+                a = 0u; ta = zero4;                             // out of range: empty planes AND a zero table
+                if (live && w < words && ks < p.ksteps) {
+                    a = __ldg(crow + w);
+                    const int k = p.wpb_shift >= 0 ? (w >> p.wpb_shift) : (int)__umulhi((uint32_t)w, p.wpb_magic);
+                    ta = __ldg(trow + min(k, p.nb - 1));
                 }
             };
-            uint32_t w0, w1, n0, n1;
-            float4 ta, tb, na, nb4;
-            fetch(0, w0, w1, ta, tb);
-            fetch(1, n0, n1, na, nb4);
+            uint32_t w0, n0;
+            float4 ta, na;
+            fetch(0, w0, ta);
+            fetch(1, n0, na);
             for (int ks = 0; ks < p.ksteps; ++ks) {
-                uint32_t f0, f1;
-                float4 fa, fb;
-                fetch(ks + 2, f0, f1, fa, fb);
-                uint32_t qa[8], qb[8];
+                uint32_t f0;
+                float4 fa;
+                fetch(ks + 2, f0, fa);
+                uint32_t qa[8];
                 tg_expand_word(w0, tg_bits<HT>(ta.x), tg_bits<HT>(ta.y), tg_bits<HT>(ta.z), qa);
-                tg_expand_word(w1, tg_bits<HT>(tb.x), tg_bits<HT>(tb.y), tg_bits<HT>(tb.z), qb);
                 mbar_wait(empty_bar(stage), phase ^ 1);
                 const uint32_t srow = s_base + stage * TG_STAGE_BYTES + row * 128;
-                const int c0 = 4 * h;                        // this thread's four 16-byte chunks of the 128-byte row
+                const int c0 = 2 * h;                        // this thread's two 16-byte chunks of the 128-byte row
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((c0 + 0) ^ (row & 7)) << 4)),
                              "r"(qa[0]), "r"(qa[1]), "r"(qa[2]), "r"(qa[3]) : "memory");
                 asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((c0 + 1) ^ (row & 7)) << 4)),
                              "r"(qa[4]), "r"(qa[5]), "r"(qa[6]), "r"(qa[7]) : "memory");
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((c0 + 2) ^ (row & 7)) << 4)),
-                             "r"(qb[0]), "r"(qb[1]), "r"(qb[2]), "r"(qb[3]) : "memory");
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + (((c0 + 3) ^ (row & 7)) << 4)),
-                             "r"(qb[4]), "r"(qb[5]), "r"(qb[6]), "r"(qb[7]) : "memory");
                 fence_proxy_async_smem();                    // generic-proxy writes -> visible to the tensor core's async proxy
                 __syncwarp();
-                if (lane == 0) mbar_arrive(fullw_bar(stage)); // one arrival per warp: 256 arrivals on one barrier serialise
-                w0 = n0; w1 = n1; ta = na; tb = nb4;
-                n0 = f0; n1 = f1; na = fa; nb4 = fb;
+                if (lane == 0) mbar_arrive(fullw_bar(stage)); // one arrival per warp: 512 arrivals on one barrier would serialise
+                w0 = n0; ta = na;
+                n0 = f0; na = fa;
                 if (++stage == TG_STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -283,10 +280,11 @@ extern "C" int tq_tl_gemm_tc(const uint32_t* codes, int64_t wpr, const float* wt
     p.wpr = wpr;
     p.wtab = reinterpret_cast<const float4*>(wtab);
     p.n = (int)n; p.m = (int)m; p.nb = (int)ceil_div(m, block); p.block = (int)block; p.M = (int)M;
-    p.wpb = (int)(block / 16);
+    const uint32_t wpb = (uint32_t)(block / 16);
     p.wpb_shift = -1;
-    for (int sft = 0; sft < 20; ++sft)
-        if ((1 << sft) == p.wpb) p.wpb_shift = sft;
+    for (int sft = 0; sft < 28; ++sft)
+        if ((1u << sft) == wpb) p.wpb_shift = sft;
+    p.wpb_magic = wpb > 1 ? (uint32_t)(((1ull << 32) + wpb - 1) / wpb) : 0u;
     p.row_tiles = (int)ceil_div(n, TG_BM);
     p.tok_tiles = (int)ceil_div(M, bn);
     p.ksteps = (int)ceil_div(m, TG_BK);

@@ -29,8 +29,9 @@
 
 namespace tq {
 
-constexpr int TL_THREADS = 1024;          // gemv CTA: 32 warps = 32 rows
-constexpr int TL_ENTRIES = 4096;          // floats of lookup table per nibble value set: positions per chunk * tokens = 4096
+constexpr int TL_THREADS = 512;           // gemv CTA: 16 warps = 16 rows; two or three CTAs per SM overlap their phases
+constexpr int TL_ROWS = TL_THREADS / 32;
+constexpr int TL_ENTRIES = 4096;          // positions per chunk * tokens (64 KB of table per CTA)
 
 __global__ void __launch_bounds__(256)
 tl_pack_kernel(const int8_t* __restrict__ Torig, int64_t n, int64_t m, const int32_t* __restrict__ perm,
@@ -78,49 +79,35 @@ __device__ __forceinline__ float tl_pick(const float4& wt, uint32_t word, int j)
 }
 
 // Lookup table of one chunk: KC = TL_ENTRIES / MT positions = KC/4 groups of 4 positions; 128 groups (512 positions,
-// the 32 code words one warp step reads) form a segment.  Entry (segment s, nibble v, group gl of the segment, token t)
-// lives at  tab[((s * 16 + v) * 128 + col(gl)) * MT + t],  col(gl) = (gl & ~31) | ((gl + (gl >> 5)) & 31):
-// lane l looks up groups 4l + i, i.e. columns 32a + ((4b + i + a) & 31) with l = 8a + b -- 32 distinct banks.
+// the 32 code words one warp step reads) form a segment.  Entry (token t, segment s, nibble v, group gl of the segment)
+// is the float at  tab[((t * SEGS + s) * 16 + v) * 128 + col(gl)],  col(gl) = (gl & ~31) | ((gl + (gl >> 5)) & 31):
+// lane l looks up groups 4l + i, i.e. columns 32a + ((4b + i + a) & 31) with l = 8a + b -- 32 distinct banks for every
+// nibble value, so a lookup is one conflict-free 4-byte shared load per token.
 __device__ __forceinline__ int tl_col(int gl) { return (gl & ~31) | ((gl + (gl >> 5)) & 31); }
 
-template <int MT> struct TlVec;
-template <> struct TlVec<1> { using type = float; };
-template <> struct TlVec<2> { using type = float2; };
-template <> struct TlVec<4> { using type = float4; };
-
-template <int MT>
-__device__ __forceinline__ void tl_lookup_add(const float* tab, int index, float (&acc)[MT]) {
-    const typename TlVec<MT>::type v = *reinterpret_cast<const typename TlVec<MT>::type*>(tab + (size_t)index * MT);
-    if constexpr (MT == 1) { acc[0] += v; }
-    else if constexpr (MT == 2) { acc[0] += v.x; acc[1] += v.y; }
-    else { acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w; }
-}
-
 template <typename XT, int MT>
-__global__ void __launch_bounds__(TL_THREADS, 1)
+__global__ void __launch_bounds__(TL_THREADS, 2)
 tl_gemv_kernel(const uint32_t* __restrict__ codes, int64_t wpr, const float4* __restrict__ wtab, int n, int m, int nb,
-               int wpb, int wpb_shift, const XT* __restrict__ x, int64_t ldx, int M, const int32_t* __restrict__ perm,
-               const float* __restrict__ bias, float* __restrict__ y, int64_t ldy) {
+               int wpb_shift, uint32_t wpb_magic, const XT* __restrict__ x, int64_t ldx, int M,
+               const int32_t* __restrict__ perm, const float* __restrict__ bias, float* __restrict__ y, int64_t ldy) {
     constexpr int KC = TL_ENTRIES / MT;          // positions per chunk
-    constexpr int GPC = KC / 4;                  // groups per chunk (= threads per token in the build phase)
+    constexpr int GPC = KC / 4;                  // groups per chunk
     constexpr int SEGS = KC / 512;               // warp steps per chunk
+    constexpr int TOK_BYTES = SEGS * 16 * 128 * 4;   // one token's table
     extern __shared__ __align__(16) float tl_smem[];
-    float* tab = tl_smem;                        // [SEGS][16][128][MT]
-    float* wsum = tl_smem + (size_t)SEGS * 16 * 128 * MT;      // [KC/16][MT] sum of the 16 inputs of each code word
+    float* tab = tl_smem;                        // [MT][SEGS][16][128]
+    float* wsum = tl_smem + MT * SEGS * 16 * 128;   // [MT][KC/16] sum of the 16 inputs of each code word
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int r = blockIdx.x * 32 + warp;
+    const int r = blockIdx.x * TL_ROWS + warp;
     const bool live = r < n;
     const int words = (m + 15) >> 4;
     const uint32_t* crow = codes + (int64_t)(live ? r : 0) * wpr;
     const float4* trow = wtab + (int64_t)(live ? r : 0) * nb;
 
-    int colbase[4];                              // table column of this lane's i-th group within a segment
+    uint32_t cb[4];                              // byte offset of this lane's i-th group column within a nibble row
 #pragma unroll
-    for (int i = 0; i < 4; ++i) colbase[i] = tl_col(4 * lane + i);
-
-    // build-phase role: (token bt, group bg of the chunk)
-    const int bt = threadIdx.x / GPC, bg = threadIdx.x - bt * GPC;
+    for (int i = 0; i < 4; ++i) cb[i] = (uint32_t)tl_col(4 * lane + i) * 4u;
 
     float acc[MT];
 #pragma unroll
@@ -135,8 +122,10 @@ tl_gemv_kernel(const uint32_t* __restrict__ codes, int64_t wpr, const float4* __
             wd[s] = (live && w < words) ? __ldg(crow + w) : 0u;
         }
         __syncthreads();                         // previous chunk's table fully consumed
-        {
-            // the 16 subset sums of inputs 4 bg .. 4 bg + 3 of token bt (entry v = sum of x_j over the bits j of v)
+        // build: item = (token bt, group bg); the 16 subset sums of inputs 4 bg .. 4 bg + 3 (entry v = sum over the bits of v)
+#pragma unroll
+        for (int item = threadIdx.x; item < GPC * MT; item += TL_THREADS) {
+            const int bt = item / GPC, bg = item - bt * GPC;
             float xv[4];
             const int p0 = c0 + 4 * bg;
 #pragma unroll
@@ -154,40 +143,49 @@ tl_gemv_kernel(const uint32_t* __restrict__ codes, int64_t wpr, const float4* __
                 const int j = (low == 1) ? 0 : (low == 2) ? 1 : (low == 4) ? 2 : 3;
                 e[v] = e[v ^ low] + xv[j];
             }
-            const int seg = bg >> 7, col = tl_col(bg & 127);
-            float* dst = tab + ((size_t)(seg * 16) * 128 + col) * MT + bt;
+            float* dst = tab + ((bt * SEGS + (bg >> 7)) * 16) * 128 + tl_col(bg & 127);
 #pragma unroll
-            for (int v = 0; v < 16; ++v) dst[(size_t)v * 128 * MT] = e[v];
+            for (int v = 0; v < 16; ++v) dst[v * 128] = e[v];
             // word totals: groups 4q .. 4q+3 are adjacent lanes
             float tot = e[15];
             tot += __shfl_xor_sync(0xffffffffu, tot, 1);
             tot += __shfl_xor_sync(0xffffffffu, tot, 2);
-            if ((bg & 3) == 0) wsum[(bg >> 2) * MT + bt] = tot;
+            if ((bg & 3) == 0) wsum[bt * (KC / 16) + (bg >> 2)] = tot;
         }
         __syncthreads();
         if (live) {
+            const char* tabc = reinterpret_cast<const char*>(tab);
 #pragma unroll
             for (int s = 0; s < SEGS; ++s) {
                 const int wl = 32 * s + lane;                              // word within the chunk
                 const int w = (c0 >> 4) + wl;
                 if (w >= words) continue;
                 const uint32_t word = wd[s];
-                const float* seg = tab + (size_t)s * 16 * 128 * MT;
-                float sp[MT], sn[MT];
-#pragma unroll
-                for (int t = 0; t < MT; ++t) { sp[t] = 0.f; sn[t] = 0.f; }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    tl_lookup_add<MT>(seg, (int)((word >> (4 * i)) & 15u) * 128 + colbase[i], sp);
-                    tl_lookup_add<MT>(seg, (int)((word >> (16 + 4 * i)) & 15u) * 128 + colbase[i], sn);
-                }
-                const int k = wpb_shift >= 0 ? (w >> wpb_shift) : (w / wpb);      // code words per block: usually 8
-                const float4 wt = __ldg(trow + min(k, nb - 1));
+                const char* seg = tabc + s * (16 * 128 * 4);
+                // byte offset of (nibble value, column): value * 512 | column * 4
+                uint32_t op[4], on[4];
+                op[0] = ((word << 9) & 0x1E00u) | cb[0];
+                op[1] = ((word << 5) & 0x1E00u) | cb[1];
+                op[2] = ((word << 1) & 0x1E00u) | cb[2];
+                op[3] = ((word >> 3) & 0x1E00u) | cb[3];
+                on[0] = ((word >> 7) & 0x1E00u) | cb[0];
+                on[1] = ((word >> 11) & 0x1E00u) | cb[1];
+                on[2] = ((word >> 15) & 0x1E00u) | cb[2];
+                on[3] = ((word >> 19) & 0x1E00u) | cb[3];
+                const uint32_t k = wpb_shift >= 0 ? ((uint32_t)w >> wpb_shift) : __umulhi((uint32_t)w, wpb_magic);
+                const float4 wt = __ldg(trow + min((int)k, nb - 1));
                 const float dp = __fsub_rn(wt.z, wt.y), dn = __fsub_rn(wt.x, wt.y);
 #pragma unroll
                 for (int t = 0; t < MT; ++t) {
-                    const float tot = wsum[wl * MT + t];
-                    acc[t] = fmaf(wt.y, tot, fmaf(dp, sp[t], fmaf(dn, sn[t], acc[t])));
+                    const char* tk = seg + t * TOK_BYTES;
+                    float sp = 0.f, sn = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        sp += *reinterpret_cast<const float*>(tk + op[i]);
+                        sn += *reinterpret_cast<const float*>(tk + on[i]);
+                    }
+                    const float tot = wsum[t * (KC / 16) + wl];
+                    acc[t] = fmaf(wt.y, tot, fmaf(dp, sp, fmaf(dn, sn, acc[t])));
                 }
             }
         }
@@ -205,30 +203,36 @@ template <> __device__ __forceinline__ __half tl_cast<__half>(float v) { return 
 template <> __device__ __forceinline__ __nv_bfloat16 tl_cast<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 template <> __device__ __forceinline__ int8_t tl_cast<int8_t>(float v) { return (int8_t)v; }
 
-// one thread per PAIR of positions, consecutive threads = consecutive pairs of one row (grid.y strides over rows): with the
-// identity order a warp writes 64 consecutive elements; wtab == nullptr expands to T
+// One thread per PAIR of output columns, consecutive threads = consecutive pairs of one row (grid.y strides over rows), so
+// a warp writes 64 consecutive elements.  Identity order: column = position.  Permuted layer with inv_perm: the thread
+// GATHERS the code of position inv_perm[column] (the row's code words are 1-3 KB, L1-resident) and the writes stay
+// coalesced; with perm only it falls back to scattering position p to column perm[p].  wtab == nullptr expands to T.
 template <typename OT>
 __global__ void __launch_bounds__(256)
 tl_expand_kernel(const uint32_t* __restrict__ codes, int64_t wpr, const float4* __restrict__ wtab, int n, int m, int nb,
-                 int wpb, int wpb_shift, const int32_t* __restrict__ perm, OT* __restrict__ out, int64_t ldo) {
+                 int wpb_shift, uint32_t wpb_magic, const int32_t* __restrict__ perm, const int32_t* __restrict__ inv_perm,
+                 OT* __restrict__ out, int64_t ldo) {
     const int pairs = (m + 1) >> 1;
+    const float4 unit = make_float4(-1.f, 0.f, 1.f, 0.f);
     for (int r = blockIdx.y; r < n; r += gridDim.y) {
         const uint32_t* crow = codes + (int64_t)r * wpr;
+        const float4* trow = wtab ? wtab + (int64_t)r * nb : nullptr;
         OT* row = out + (int64_t)r * ldo;
+        auto value = [&](int p) {
+            const int w = p >> 4;
+            const uint32_t k = wpb_shift >= 0 ? ((uint32_t)w >> wpb_shift) : __umulhi((uint32_t)w, wpb_magic);
+            const float4 wt = trow ? __ldg(trow + min((int)k, nb - 1)) : unit;
+            return tl_cast<OT>(tl_pick(wt, __ldg(crow + w), p & 15));
+        };
         for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < pairs; q += gridDim.x * blockDim.x) {
-            const int p0 = q * 2;
-            const int w = p0 >> 4, j = p0 & 15;
-            const uint32_t word = __ldg(crow + w);
-            const int k = min(wpb_shift >= 0 ? (w >> wpb_shift) : (w / wpb), nb - 1);
-            const float4 wt = wtab ? __ldg(wtab + (int64_t)r * nb + k) : make_float4(-1.f, 0.f, 1.f, 0.f);
-            const OT v0 = tl_cast<OT>(tl_pick(wt, word, j));
-            const OT v1 = tl_cast<OT>(tl_pick(wt, word, j + 1));
-            if (perm) {
-                row[perm[p0]] = v0;
-                if (p0 + 1 < m) row[perm[p0 + 1]] = v1;
+            const int c0 = q * 2;
+            const bool two = c0 + 1 < m;
+            if (perm && !inv_perm) {                       // scatter
+                row[perm[c0]] = value(c0);
+                if (two) row[perm[c0 + 1]] = value(c0 + 1);
             } else {
-                row[p0] = v0;
-                if (p0 + 1 < m) row[p0 + 1] = v1;
+                row[c0] = value(inv_perm ? inv_perm[c0] : c0);
+                if (two) row[c0 + 1] = value(inv_perm ? inv_perm[c0 + 1] : c0 + 1);
             }
         }
     }
@@ -236,14 +240,15 @@ tl_expand_kernel(const uint32_t* __restrict__ codes, int64_t wpr, const float4* 
 
 template <typename OT>
 static int launch_expand(const uint32_t* codes, int64_t wpr, const float4* wt, int64_t n, int64_t m, int64_t nb, int64_t block,
-                         const int32_t* perm, OT* out, int64_t ldo, cudaStream_t st) {
-    const int wpb = (int)(block / 16) > 0 ? (int)(block / 16) : 1;
+                         const int32_t* perm, const int32_t* inv_perm, OT* out, int64_t ldo, cudaStream_t st) {
+    const uint32_t wpb = block / 16 > 0 ? (uint32_t)(block / 16) : 1u;
     int wpb_shift = -1;
     for (int sft = 0; sft < 28; ++sft)
-        if ((1 << sft) == wpb) wpb_shift = sft;
+        if ((1u << sft) == wpb) wpb_shift = sft;
+    const uint32_t magic = wpb > 1 ? (uint32_t)(((1ull << 32) + wpb - 1) / wpb) : 0u;
     const int64_t pairs = (m + 1) / 2;
     dim3 grid((unsigned)(ceil_div(pairs, 256) < 32 ? ceil_div(pairs, 256) : 32), (unsigned)(n < 65535 ? n : 65535));
-    tl_expand_kernel<OT><<<grid, 256, 0, st>>>(codes, wpr, wt, (int)n, (int)m, (int)nb, wpb, wpb_shift, perm, out, ldo);
+    tl_expand_kernel<OT><<<grid, 256, 0, st>>>(codes, wpr, wt, (int)n, (int)m, (int)nb, wpb_shift, magic, perm, inv_perm, out, ldo);
     TQ_LAUNCH_CHECK("tl_expand_kernel");
     return 0;
 }
@@ -256,7 +261,7 @@ static inline unsigned tl_grid(int64_t work, int threads) {
     return (unsigned)g;
 }
 
-template <int MT> constexpr int tl_gemv_smem() { return (TL_ENTRIES / MT / 512) * 16 * 128 * MT * 4 + (TL_ENTRIES / MT / 16) * MT * 4; }
+template <int MT> constexpr int tl_gemv_smem() { return TL_ENTRIES * 4 * 4 + (TL_ENTRIES / 16) * 4; }
 
 template <typename XT, int MT>
 static int launch_gemv_mt(const uint32_t* codes, int64_t wpr, const float4* wt, int64_t n, int64_t m, int64_t nb,
@@ -268,12 +273,15 @@ static int launch_gemv_mt(const uint32_t* codes, int64_t wpr, const float4* wt, 
         TQ_CUDA(cudaFuncSetAttribute(tl_gemv_kernel<XT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
-    const int wpb = (int)(block / 16);
+    // block index of code word w = w / (block / 16): a shift, or a multiply-high by ceil(2^32 / wpb) (exact for
+    // w * wpb < 2^32, i.e. any m < 2^31)
+    const uint32_t wpb = (uint32_t)(block / 16);
     int wpb_shift = -1;
-    for (int sft = 0; sft < 20; ++sft)
-        if ((1 << sft) == wpb) wpb_shift = sft;
-    tl_gemv_kernel<XT, MT><<<(unsigned)ceil_div(n, 32), TL_THREADS, smem, st>>>(codes, wpr, wt, (int)n, (int)m, (int)nb, wpb,
-                                                                               wpb_shift, x, ldx, mt, perm, bias, y, ldy);
+    for (int sft = 0; sft < 28; ++sft)
+        if ((1u << sft) == wpb) wpb_shift = sft;
+    const uint32_t magic = wpb > 1 ? (uint32_t)(((1ull << 32) + wpb - 1) / wpb) : 0u;
+    tl_gemv_kernel<XT, MT><<<(unsigned)ceil_div(n, TL_ROWS), TL_THREADS, smem, st>>>(
+        codes, wpr, wt, (int)n, (int)m, (int)nb, wpb_shift, magic, x, ldx, mt, perm, bias, y, ldy);
     TQ_LAUNCH_CHECK("tl_gemv_kernel");
     return 0;
 }
@@ -351,7 +359,7 @@ extern "C" int tq_tl_gemv(const uint32_t* codes, int64_t wpr, const float* wtab,
 }
 
 extern "C" int tq_tl_dequant(const uint32_t* codes, int64_t wpr, const float* wtab, int64_t n, int64_t m, int64_t block,
-                             const int32_t* perm, void* W, int wdtype, int64_t ldw, void* stream) {
+                             const int32_t* perm, const int32_t* inv_perm, void* W, int wdtype, int64_t ldw, void* stream) {
     using namespace tq;
     TQ_CHECK_ARG(codes && wtab && W && n > 0 && m > 0 && wpr >= ceil_div(m, 16) && ldw >= m, "tq_tl_dequant: bad arguments");
     if (block <= 0 || block % 16 != 0) {
@@ -363,17 +371,18 @@ extern "C" int tq_tl_dequant(const uint32_t* codes, int64_t wpr, const float* wt
     const int64_t nb = ceil_div(m, block);
     cudaStream_t st = (cudaStream_t)stream;
     const float4* wt = reinterpret_cast<const float4*>(wtab);
-    if (wdtype == TQ_F32) return launch_expand<float>(codes, wpr, wt, n, m, nb, block, perm, (float*)W, ldw, st);
-    if (wdtype == TQ_F16) return launch_expand<__half>(codes, wpr, wt, n, m, nb, block, perm, (__half*)W, ldw, st);
-    if (wdtype == TQ_BF16) return launch_expand<__nv_bfloat16>(codes, wpr, wt, n, m, nb, block, perm, (__nv_bfloat16*)W, ldw, st);
+    if (wdtype == TQ_F32) return launch_expand<float>(codes, wpr, wt, n, m, nb, block, perm, inv_perm, (float*)W, ldw, st);
+    if (wdtype == TQ_F16) return launch_expand<__half>(codes, wpr, wt, n, m, nb, block, perm, inv_perm, (__half*)W, ldw, st);
+    if (wdtype == TQ_BF16) return launch_expand<__nv_bfloat16>(codes, wpr, wt, n, m, nb, block, perm, inv_perm, (__nv_bfloat16*)W, ldw, st);
     set_error("tq_tl_dequant: unknown dtype %d", wdtype);
     return TQ_E_BADARG;
 }
 
-extern "C" int tq_tl_unpack(const uint32_t* codes, int64_t wpr, int64_t n, int64_t m, const int32_t* perm, int8_t* Torig,
-                            void* stream) {
+extern "C" int tq_tl_unpack(const uint32_t* codes, int64_t wpr, int64_t n, int64_t m, const int32_t* perm,
+                            const int32_t* inv_perm, int8_t* Torig, void* stream) {
     using namespace tq;
     TQ_CHECK_ARG(codes && Torig && n > 0 && m > 0 && wpr >= ceil_div(m, 16), "tq_tl_unpack: bad arguments");
     TQ_CHECK_ARG(n < (1ll << 31) && m < (1ll << 31) - 2, "tq_tl_unpack: shape too large");
-    return launch_expand<int8_t>(codes, wpr, nullptr, n, m, 1, ((m + 15) / 16) * 16, perm, Torig, m, (cudaStream_t)stream);
+    return launch_expand<int8_t>(codes, wpr, nullptr, n, m, 1, ((m + 15) / 16) * 16, perm, inv_perm, Torig, m,
+                                 (cudaStream_t)stream);
 }

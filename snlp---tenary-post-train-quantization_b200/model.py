@@ -63,7 +63,7 @@ class TernaryLinear(nn.Module):
             self.register_buffer("bias", torch.zeros(out_features, dtype=dtype, device=device))
         else:
             self.bias = None
-        self._derived = None          # (wtab f32 [n, nb, 4], perm int32 or None, bias f32 or None), rebuilt lazily
+        self._derived = None          # (wtab f32 [n, nb, 4], perm / inv_perm int32 or None, bias f32 or None), rebuilt lazily
         self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
 
     # ------------------------------------------------------------------ parameters
@@ -112,8 +112,9 @@ class TernaryLinear(nn.Module):
                                       _lib.ptr(wtab), _lib.stream()), "tq_tl_wtab")
         identity = bool(torch.equal(self.perm, torch.arange(self.in_features, device=dev)))
         perm32 = None if identity else self.perm.to(torch.int32).contiguous()
+        inv32 = None if identity else torch.argsort(self.perm).to(torch.int32).contiguous()
         bias32 = None if self.bias is None else self.bias.float().contiguous()
-        self._derived = (wtab, perm32, bias32)
+        self._derived = (wtab, perm32, bias32, inv32)
         return self._derived
 
     @property
@@ -121,25 +122,25 @@ class TernaryLinear(nn.Module):
         """int8 (n, m) ternary matrix in original column positions (the reference's buffer, model.py:43)."""
         lib = _lib.load()
         _lib.require_cuda(self.codes, "TernaryLinear buffers")
-        _, perm32, _ = self._prepared()
+        _, perm32, _, inv32 = self._prepared()
         n, m = self.out_features, self.in_features
         out = torch.empty((n, m), dtype=torch.int8, device=self.codes.device)
         with torch.cuda.device(self.codes.device):
-            _lib.check(lib.tq_tl_unpack(_lib.ptr(self.codes), self.codes.shape[1], n, m, _lib.ptr(perm32), _lib.ptr(out),
-                                        _lib.stream()), "tq_tl_unpack")
+            _lib.check(lib.tq_tl_unpack(_lib.ptr(self.codes), self.codes.shape[1], n, m, _lib.ptr(perm32), _lib.ptr(inv32),
+                                        _lib.ptr(out), _lib.stream()), "tq_tl_unpack")
         return out
 
     # ------------------------------------------------------------------ forward
     def _dequantize(self) -> torch.Tensor:
         """Dense weight (n, m) in the layer dtype, original column positions (gptq.py:201-230 semantics)."""
         lib = _lib.load()
-        wtab, perm32, _ = self._prepared()
+        wtab, perm32, _, inv32 = self._prepared()
         n, m = self.out_features, self.in_features
         W = torch.empty((n, m), dtype=self.alpha.dtype, device=self.codes.device)
         with torch.cuda.device(self.codes.device):
             _lib.check(lib.tq_tl_dequant(_lib.ptr(self.codes), self.codes.shape[1], _lib.ptr(wtab), n, m, self.block_size,
-                                         _lib.ptr(perm32), _lib.ptr(W), _lib.dtype_code(W.dtype), m, _lib.stream()),
-                       "tq_tl_dequant")
+                                         _lib.ptr(perm32), _lib.ptr(inv32), _lib.ptr(W), _lib.dtype_code(W.dtype), m,
+                                         _lib.stream()), "tq_tl_dequant")
         return W
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
@@ -157,7 +158,7 @@ class TernaryLinear(nn.Module):
                 return self._forward_fused(x2.to(dtype)).reshape(*lead, self.out_features)
             out = torch.nn.functional.linear(x2.to(dtype), self._dequantize(), self.bias)
             return out.reshape(*lead, self.out_features)
-        wtab, perm32, bias32 = self._prepared()
+        wtab, perm32, bias32, _ = self._prepared()
         if x2.dtype not in (torch.float32, torch.float16, torch.bfloat16):
             x2 = x2.to(dtype)
         if x2.stride(-1) != 1:
@@ -173,7 +174,7 @@ class TernaryLinear(nn.Module):
     def _forward_fused(self, x2: torch.Tensor) -> torch.Tensor:
         """Many tokens, 16-bit layer: one tcgen05 GEMM that expands the codes in shared memory (tq_tl_gemm_tc)."""
         lib = _lib.load()
-        wtab, perm32, bias32 = self._prepared()
+        wtab, perm32, bias32, _ = self._prepared()
         if x2.stride(-1) != 1 or (x2.stride(0) * 2) % 16 != 0 or x2.data_ptr() % 16 != 0:
             x2 = x2.contiguous()
         tokens = x2.shape[0]

@@ -71,10 +71,12 @@ def test_tl_pack_unpack_bit_exact(G, n, m):
         codes, pd = _pack(G, T, p)
         want = otl.pack_layer(T, np.arange(m) if p is None else p)
         assert np.array_equal(codes.cpu().numpy().view(np.uint32), want)
-        out = torch.empty((n, m), dtype=torch.int8, device=G.DEV)
-        _lib.check(L.tq_tl_unpack(_lib.ptr(codes), codes.shape[1], n, m, _lib.ptr(pd), _lib.ptr(out), _lib.stream()),
-                   "tq_tl_unpack")
-        assert np.array_equal(out.cpu().numpy(), T)
+        inv = None if p is None else G.i32(np.argsort(p))
+        for ip in ((None,) if p is None else (None, inv)):          # scatter by perm / gather by inv_perm
+            out = torch.full((n, m), 7, dtype=torch.int8, device=G.DEV)
+            _lib.check(L.tq_tl_unpack(_lib.ptr(codes), codes.shape[1], n, m, _lib.ptr(pd), _lib.ptr(ip), _lib.ptr(out),
+                                      _lib.stream()), "tq_tl_unpack")
+            assert np.array_equal(out.cpu().numpy(), T)
 
 
 @pytest.mark.parametrize("dtype", ["float32", "float16", "bfloat16"])
@@ -86,11 +88,13 @@ def test_tl_wtab_and_dequant_bit_exact(G, dtype):
     wtab = _wtab(G, alpha, mu, dtype)
     assert np.array_equal(wtab.cpu().numpy(), otl.weight_table(alpha, mu, dtype))
     codes, pd = _pack(G, T, perm)
-    W = torch.empty((n, m), dtype=TDT[dtype], device=G.DEV)
-    _lib.check(L.tq_tl_dequant(_lib.ptr(codes), codes.shape[1], _lib.ptr(wtab), n, m, block, _lib.ptr(pd), _lib.ptr(W),
-                               _lib.dtype_code(TDT[dtype]), m, _lib.stream()), "tq_tl_dequant")
     want = otl.dequantized_weight(alpha, mu, T, perm, block, dtype)
-    assert np.array_equal(W.float().cpu().numpy().astype(np.float64), want)
+    inv = G.i32(np.argsort(perm))
+    for ip in (None, inv):                                          # scatter by perm / gather by inv_perm
+        W = torch.zeros((n, m), dtype=TDT[dtype], device=G.DEV)
+        _lib.check(L.tq_tl_dequant(_lib.ptr(codes), codes.shape[1], _lib.ptr(wtab), n, m, block, _lib.ptr(pd), _lib.ptr(ip),
+                                   _lib.ptr(W), _lib.dtype_code(TDT[dtype]), m, _lib.stream()), "tq_tl_dequant")
+        assert np.array_equal(W.float().cpu().numpy().astype(np.float64), want)
 
 
 @pytest.mark.parametrize("xdtype", ["float32", "float16", "bfloat16"])
