@@ -3,15 +3,16 @@
 // every forward, model.py:87, :97-110).
 //
 //   D[128 weight rows, 256 tokens] (fp32, TMEM) += A[128 x 64] * B[256 x 64]',  kind::f16, UMMA 128x256x16
-//   (128-token tiles, UMMA 128x128x16, when 256-token tiles would leave SMs without work)
+//   (tile widths of 128 / 256 / 512 tokens; a 512-token tile issues two 256-wide MMAs per K step on one A slab)
 //   A = dequantised weights, K-major, 128B-swizzled, WRITTEN BY SIXTEEN DEQUANT WARPS from the TL2 code words
 //       (ternary_linear.cu): value = wtab[row, p/block][code], already rounded to the layer's 16-bit dtype, so the
 //       tensor core multiplies exactly the reference's fp16/bf16 weight `alpha * T + mu`;
 //   B = activations [tokens, m] in sweep order (gathered by perm beforehand when perm is not the identity,
 //       model.py:84), K-major, fetched by TMA (one 256 x 64 box per stage, out-of-range rows/columns zero-filled);
-//   pipeline: 4 smem stages x (A 16 KB + B 32 KB); per stage two "full" barriers (TMA bytes; one arrival per
+//   pipeline: 4 smem stages x (A 16 KB + B 32 KB), or 2 x (16 + 64 KB) for 512-token tiles; per stage two "full" barriers (TMA bytes; one arrival per
 //       dequant warp after every lane's fence.proxy.async) and one "empty" barrier (tcgen05.commit) that both producers wait on;
-//   TMEM: 2 accumulators x 256 columns, so the epilogue of one tile overlaps the MMAs of the next;
+//   TMEM: 2 accumulators x 256 columns, so the epilogue of one tile overlaps the MMAs of the next (512-token tiles
+//       use all 512 columns for one accumulator);
 //   epilogue: tcgen05.ld -> (+ bias) -> 16-bit stores y[token, row] with lanes along the rows (contiguous in y);
 //   schedule: persistent CTAs; tiles ordered token-tile-major so concurrently running CTAs share the same x slab in L2.
 //   roles: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 epilogue, warps 8-23 dequant
@@ -20,13 +21,19 @@
 
 namespace tq {
 
-constexpr int TG_BM = 128, TG_BK = 64, TG_STAGES = 4, TG_UMMA_K = 16;
+constexpr int TG_BM = 128, TG_BK = 64, TG_UMMA_K = 16;
 constexpr int TG_A_BYTES = TG_BM * TG_BK * 2;                 // 16384
-constexpr int TG_STAGE_BYTES = TG_A_BYTES + 256 * TG_BK * 2;  // 49152: A + the widest B tile (256 tokens)
+constexpr int TG_MAX_STAGES = 4;
+// token-tile width -> pipeline geometry: <= 256 tokens: 4 stages x (A 16 KB + B 32 KB) = 192 KB, two TMEM accumulators;
+// 512 tokens: 2 stages x (A 16 KB + B 64 KB) = 160 KB, ONE 512-column accumulator (two 256-wide MMAs per K step share
+// the dequantised A slab, halving the expansion work per MMA; the epilogue is then not overlapped with the next tile)
+__host__ __device__ constexpr int tg_stages(int bn) { return bn == 512 ? 2 : 4; }
+__host__ __device__ constexpr int tg_stage_bytes(int bn) { return TG_A_BYTES + (bn == 512 ? 512 : 256) * TG_BK * 2; }
+__host__ __device__ constexpr int tg_acc_bufs(int bn) { return bn == 512 ? 1 : 2; }
 constexpr int TG_THREADS = 768;
 constexpr int TG_DEQ_THREADS = 512;
 constexpr int TG_DEQ_WARPS = TG_DEQ_THREADS / 32;
-constexpr int TG_SMEM = TG_STAGES * TG_STAGE_BYTES + 256 + 1024;
+constexpr int TG_SMEM = 4 * tg_stage_bytes(256) + 256 + 1024;          // >= 2 * tg_stage_bytes(512)
 
 struct TgProblem {
     const uint32_t* codes;
@@ -65,20 +72,25 @@ __device__ __forceinline__ void tg_expand_word(uint32_t word, uint32_t h0, uint3
     }
 }
 
-// TG_BN = tokens per tile: 256, or 128 when 256-token tiles would leave SMs without work
+// TG_BN = tokens per tile (128 / 256 / 512), chosen by the host to minimise the number of tile waves
 template <typename HT, int TG_BN>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 tl_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TgProblem p, uint32_t idesc) {
+    constexpr int TG_STAGES = tg_stages(TG_BN);
+    constexpr int TG_STAGE_BYTES = tg_stage_bytes(TG_BN);
+    constexpr int NBUF = tg_acc_bufs(TG_BN);                  // accumulator buffers in TMEM
+    constexpr int BOX = TG_BN < 256 ? TG_BN : 256;            // tokens per TMA box and per MMA
+    constexpr int NBOX = TG_BN / BOX;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t s_base = smem_u32(smem);
     const uint32_t s_bar = s_base + TG_STAGES * TG_STAGE_BYTES;
     auto fullx_bar = [&](int s) { return s_bar + 8 * s; };
-    auto fullw_bar = [&](int s) { return s_bar + 8 * (TG_STAGES + s); };
-    auto empty_bar = [&](int s) { return s_bar + 8 * (2 * TG_STAGES + s); };
-    auto tfull_bar = [&](int a) { return s_bar + 8 * (3 * TG_STAGES + a); };
-    auto tempty_bar = [&](int a) { return s_bar + 8 * (3 * TG_STAGES + 2 + a); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TG_STAGES * TG_STAGE_BYTES + 8 * (3 * TG_STAGES + 4));
+    auto fullw_bar = [&](int s) { return s_bar + 8 * (TG_MAX_STAGES + s); };
+    auto empty_bar = [&](int s) { return s_bar + 8 * (2 * TG_MAX_STAGES + s); };
+    auto tfull_bar = [&](int a) { return s_bar + 8 * (3 * TG_MAX_STAGES + a); };
+    auto tempty_bar = [&](int a) { return s_bar + 8 * (3 * TG_MAX_STAGES + 2 + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + TG_STAGES * TG_STAGE_BYTES + 8 * (3 * TG_MAX_STAGES + 4));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -88,7 +100,7 @@ tl_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TgProblem p, 
             mbar_init(fullw_bar(s), TG_DEQ_WARPS);
             mbar_init(empty_bar(s), 1);
         }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+        for (int a = 0; a < NBUF; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc_512(smem_u32(tmem_slot));
@@ -107,7 +119,10 @@ tl_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TgProblem p, 
             for (int ks = 0; ks < p.ksteps; ++ks) {
                 mbar_wait(empty_bar(stage), phase ^ 1);
                 mbar_expect_tx(fullx_bar(stage), TG_B_BYTES);
-                tma_load_2d(s_base + stage * TG_STAGE_BYTES + TG_A_BYTES, &map_x, fullx_bar(stage), ks * TG_BK, bj * TG_BN);
+#pragma unroll
+                for (int b = 0; b < NBOX; ++b)
+                    tma_load_2d(s_base + stage * TG_STAGE_BYTES + TG_A_BYTES + b * BOX * TG_BK * 2, &map_x, fullx_bar(stage),
+                                ks * TG_BK, bj * TG_BN + b * BOX);
                 if (++stage == TG_STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -115,8 +130,8 @@ tl_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TgProblem p, 
         // ===== MMA issuer =====
         int stage = 0, phase = 0, n_item = 0;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++n_item) {
-            const int acc = n_item & 1;
-            mbar_wait(tempty_bar(acc), ((n_item >> 1) & 1) ^ 1);
+            const int acc = n_item % NBUF;
+            mbar_wait(tempty_bar(acc), ((n_item / NBUF) & 1) ^ 1);
             tc_fence_after();
             const uint32_t tmem_d = tmem_base + acc * TG_BN;
             for (int ks = 0; ks < p.ksteps; ++ks) {
@@ -127,7 +142,10 @@ tl_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TgProblem p, 
                 const uint32_t sb = sa + TG_A_BYTES;
 #pragma unroll
                 for (int k = 0; k < TG_BK / TG_UMMA_K; ++k)
-                    umma_f16(tmem_d, tg_desc(sa + k * TG_UMMA_K * 2), tg_desc(sb + k * TG_UMMA_K * 2), idesc, (ks | k) != 0);
+#pragma unroll
+                    for (int b = 0; b < NBOX; ++b)
+                        umma_f16(tmem_d + b * BOX, tg_desc(sa + k * TG_UMMA_K * 2),
+                                 tg_desc(sb + b * BOX * TG_BK * 2 + k * TG_UMMA_K * 2), idesc, (ks | k) != 0);
                 umma_commit(empty_bar(stage));
                 if (ks == p.ksteps - 1) umma_commit(tfull_bar(acc));
                 if (++stage == TG_STAGES) { stage = 0; phase ^= 1; }
@@ -140,10 +158,10 @@ tl_gemm_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TgProblem p, 
         int n_item = 0;
         for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++n_item) {
             const int bj = t / p.row_tiles, bi = t - bj * p.row_tiles;
-            const int acc = n_item & 1;
+            const int acc = n_item % NBUF;
             const int r = bi * TG_BM + q * 32 + lane;
             const float bv = (p.bias && r < p.n) ? p.bias[r] : 0.f;
-            mbar_wait(tfull_bar(acc), (n_item >> 1) & 1);
+            mbar_wait(tfull_bar(acc), (n_item / NBUF) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TG_BN;
 #pragma unroll 1
@@ -267,12 +285,22 @@ extern "C" int tq_tl_gemm_tc(const uint32_t* codes, int64_t wpr, const float* wt
         return TQ_E_UNSUPPORTED;
     }
     const int sms = sm_count();
-    // 256-token tiles halve the dequantisation work per MMA; fall back to 128 when they would leave SMs idle
-    const bool wide = ceil_div(n, TG_BM) * ceil_div(M, 256) >= sms || M > 128 && ceil_div(n, TG_BM) * ceil_div(M, 128) > 2 * sms;
-    const int bn = wide ? 256 : 128;
+    // The kernel is bound by the expansion of the weight slab, which costs the same per K step whatever the tile width:
+    // time ~ (waves of tiles) x K steps.  Take the width with the fewest waves, the wider on ties (fewer CTAs, less
+    // expansion work in total), but never pad a call to more than twice its tokens.
+    int bn = 128;
+    {
+        int64_t best = ceil_div(ceil_div(n, TG_BM) * ceil_div(M, 128), sms);
+        for (int cand = 256; cand <= 512; cand *= 2) {
+            if (M <= cand / 2) break;
+            const int64_t waves = ceil_div(ceil_div(n, TG_BM) * ceil_div(M, cand), sms);
+            if (waves <= best) { best = waves; bn = cand; }
+        }
+    }
+    const int box = bn < 256 ? bn : 256;
     CUtensorMap map_x;
     int rc = make_tmap_2d(&map_x, xdtype == TQ_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, xs,
-                          M, m, lds, bn, TG_BK, "tq_tl_gemm_tc(x)");
+                          M, m, lds, box, TG_BK, "tq_tl_gemm_tc(x)");
     if (rc) return rc;
 
     TgProblem p;
@@ -293,22 +321,26 @@ extern "C" int tq_tl_gemm_tc(const uint32_t* codes, int64_t wpr, const float* wt
     p.ldy = ldy;
     const uint32_t fmt = (xdtype == TQ_F16) ? 0u : 1u;
     // tcgen05 instruction descriptor (kind::f16): D = f32, A/B format, both K-major, N = tokens per tile, M = 128
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TG_BM >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(box >> 3) << 17) | ((uint32_t)(TG_BM >> 4) << 24);
     const int64_t tiles = (int64_t)p.row_tiles * p.tok_tiles;
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
     static bool attr_set = false;
     if (!attr_set) {
+        TQ_CUDA(cudaFuncSetAttribute(tl_gemm_tc_kernel<__half, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
         TQ_CUDA(cudaFuncSetAttribute(tl_gemm_tc_kernel<__half, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
         TQ_CUDA(cudaFuncSetAttribute(tl_gemm_tc_kernel<__half, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+        TQ_CUDA(cudaFuncSetAttribute(tl_gemm_tc_kernel<__nv_bfloat16, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
         TQ_CUDA(cudaFuncSetAttribute(tl_gemm_tc_kernel<__nv_bfloat16, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
         TQ_CUDA(cudaFuncSetAttribute(tl_gemm_tc_kernel<__nv_bfloat16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
         attr_set = true;
     }
     if (xdtype == TQ_F16) {
-        if (wide) tl_gemm_tc_kernel<__half, 256><<<grid, TG_THREADS, TG_SMEM, st>>>(map_x, p, idesc);
+        if (bn == 512) tl_gemm_tc_kernel<__half, 512><<<grid, TG_THREADS, TG_SMEM, st>>>(map_x, p, idesc);
+        else if (bn == 256) tl_gemm_tc_kernel<__half, 256><<<grid, TG_THREADS, TG_SMEM, st>>>(map_x, p, idesc);
         else tl_gemm_tc_kernel<__half, 128><<<grid, TG_THREADS, TG_SMEM, st>>>(map_x, p, idesc);
     } else {
-        if (wide) tl_gemm_tc_kernel<__nv_bfloat16, 256><<<grid, TG_THREADS, TG_SMEM, st>>>(map_x, p, idesc);
+        if (bn == 512) tl_gemm_tc_kernel<__nv_bfloat16, 512><<<grid, TG_THREADS, TG_SMEM, st>>>(map_x, p, idesc);
+        else if (bn == 256) tl_gemm_tc_kernel<__nv_bfloat16, 256><<<grid, TG_THREADS, TG_SMEM, st>>>(map_x, p, idesc);
         else tl_gemm_tc_kernel<__nv_bfloat16, 128><<<grid, TG_THREADS, TG_SMEM, st>>>(map_x, p, idesc);
     }
     TQ_LAUNCH_CHECK("tl_gemm_tc_kernel");

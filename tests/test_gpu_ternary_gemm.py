@@ -44,6 +44,7 @@ def _layer(G, n, m, block, dtype, identity, bias, seed):
     (200, 1000, 128, 33, False, True),       # ragged rows, K tail (1000 = 15 slabs + 40), ragged tokens, gather
     (130, 328, 64, 257, False, False),       # block 64, m % 16 != 0 (pad codes), second token tile holds one token
     (384, 2048, 128, 17, True, True),        # smallest many-token call
+    (256, 512, 128, 200, False, True),       # 256-token tile (200 tokens are not padded to 512)
 ])
 def test_tl_gemm_tc_vs_oracle(G, n, m, block, M, identity, bias, dtype):
     layer, (alpha, mu, T, perm, b) = _layer(G, n, m, block, dtype, identity, bias, seed=n + m + M)
@@ -77,6 +78,21 @@ def test_tl_gemm_tc_persistent_tiles_match_dense_path(G):
     layer.fused_gemm = False
     y_dense = layer(x)
     assert (y.float() - y_dense.float()).abs().max().item() <= 4 * EPS["float16"] * want.abs().max().item()
+
+
+@pytest.mark.parametrize("tokens,dtype", [(256, "float16"), (512, "bfloat16"), (128, "float16")])
+def test_tl_gemm_tc_more_tiles_than_sms(G, tokens, dtype):
+    """20480 x 1024: 160 row tiles > 148 SMs, so with one token tile per row tile some CTAs run two tiles of every
+    width (128-token tiles: 1 wave... 256 tokens -> 256-wide tiles, 512 tokens -> 512-wide tiles with the single
+    accumulator reused, 128 tokens -> 128-wide tiles)."""
+    layer, _ = _layer(G, 20480, 1024, 128, dtype, False, False, seed=31)
+    gen = torch.Generator(device=G.DEV).manual_seed(tokens)
+    x = torch.randn((tokens, 1024), generator=gen, device=G.DEV).to(TDT[dtype])
+    y = layer(x)
+    W = layer._dequantize().float()
+    want = x.float() @ W.T
+    bound = EPS[dtype] * want.abs() + 2e-5 * (x.float().abs() @ W.abs().T)
+    assert torch.all((y.float() - want).abs() <= bound)
 
 
 def test_tl_gemm_tc_rejects_fp32(G):
