@@ -22,6 +22,7 @@ for rep in range(2):
     for M in (1, 4):
         layer(torch.randn((M, m), generator=gen, device=dev).half())
 x = torch.randn((512, m), generator=gen, device=dev).half()
+layer.fused_gemm = False
 layer(x)
 if os.environ.get("TL_FUSED") == "1":
     layer.fused_gemm = True

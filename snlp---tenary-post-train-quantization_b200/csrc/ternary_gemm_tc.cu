@@ -19,6 +19,8 @@
 //   (sixteen warps: the expansion is ~5 integer instructions per weight and needs the issue slots of all four schedulers).
 #include "tc_common.cuh"
 
+#include <stdlib.h>
+
 namespace tq {
 
 constexpr int TG_BM = 128, TG_BK = 64, TG_UMMA_K = 16;
@@ -285,17 +287,24 @@ extern "C" int tq_tl_gemm_tc(const uint32_t* codes, int64_t wpr, const float* wt
         return TQ_E_UNSUPPORTED;
     }
     const int sms = sm_count();
-    // The kernel is bound by the expansion of the weight slab, which costs the same per K step whatever the tile width:
-    // time ~ (waves of tiles) x K steps.  Take the width with the fewest waves, the wider on ties (fewer CTAs, less
-    // expansion work in total), but never pad a call to more than twice its tokens.
+    // The kernel is bound by the expansion of the weight slab, which costs about the same per K step whatever the tile
+    // width: time ~ (waves of tiles) x K steps x t(width), with t measured on B200 at 0.93 / 1.0 / 1.5 us for 128 / 256 /
+    // 512 tokens (profiles/r01d_tl_bench_prefill.json; the 512-wide tile has a 2-stage pipeline and no spare
+    // accumulator).  Take the cheapest width, but never pad a call to more than twice its tokens.
     int bn = 128;
     {
-        int64_t best = ceil_div(ceil_div(n, TG_BM) * ceil_div(M, 128), sms);
-        for (int cand = 256; cand <= 512; cand *= 2) {
+        const double t_step[3] = {0.93, 1.0, 1.5};
+        double best = (double)ceil_div(ceil_div(n, TG_BM) * ceil_div(M, 128), sms) * t_step[0];
+        int idx = 1;
+        for (int cand = 256; cand <= 512; cand *= 2, ++idx) {
             if (M <= cand / 2) break;
-            const int64_t waves = ceil_div(ceil_div(n, TG_BM) * ceil_div(M, cand), sms);
-            if (waves <= best) { best = waves; bn = cand; }
+            const double cost = (double)ceil_div(ceil_div(n, TG_BM) * ceil_div(M, cand), sms) * t_step[idx];
+            if (cost < best) { best = cost; bn = cand; }
         }
+    }
+    if (const char* e = getenv("TQ_TL_GEMM_BN")) {      // development / test override of the tile width
+        const int v = atoi(e);
+        if (v == 128 || v == 256 || v == 512) bn = v;
     }
     const int box = bn < 256 ? bn : 256;
     CUtensorMap map_x;

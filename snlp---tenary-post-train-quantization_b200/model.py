@@ -15,10 +15,11 @@
     tests/test_ternary_linear_cpu.py against the reference's own outputs).  For ``use_ssr=False`` results the two
     agree to rounding.
 
-Decode-sized inputs (<= ``gemv_max_tokens`` rows) go through ``tq_tl_gemv`` (reads 0.25 B per weight).  Larger
-inputs either run ``tq_tl_gemm_tc`` -- one tcgen05 GEMM that expands the codes to the layer's 16-bit dtype in shared
-memory (``fused_gemm``) -- or dequantise to a dense weight in the layer dtype (``tq_tl_dequant``) and call the library
-GEMM, like the reference's ``_dequantize`` + ``F.linear`` (fp32 layers always do).  CUDA only: no CPU fallback.
+Decode-sized inputs (<= ``gemv_max_tokens`` rows) go through ``tq_tl_gemv`` (reads 0.25 B per weight).  Up to
+``fused_max_tokens`` rows, fp16/bf16 layers run ``tq_tl_gemm_tc`` -- one tcgen05 GEMM that expands the codes to the
+layer's 16-bit dtype in shared memory, no dense weight in HBM; beyond that (and for fp32 layers) the layer
+dequantises to a dense weight in its dtype (``tq_tl_dequant``) and calls the library GEMM, like the reference's
+``_dequantize`` + ``F.linear``.  CUDA only: no CPU fallback.
 
 HF model loading (``load_model_for_quantization``, model.py:228-265) is out of scope (no network).
 """
@@ -38,7 +39,10 @@ class TernaryLinear(nn.Module):
     """model.py:17-127 on packed codes."""
 
     gemv_max_tokens = 16
-    fused_gemm = False            # many-token path: True = tq_tl_gemm_tc (fp16/bf16 layers), False = dense weight + library GEMM
+    # many-token path of fp16/bf16 layers: tq_tl_gemm_tc up to fused_max_tokens rows, dense weight + library GEMM beyond
+    # (measured crossover on B200, profiles/r01d_tl_bench_prefill.json); fused_gemm = False forces the dense path
+    fused_gemm = True
+    fused_max_tokens = 1024
 
     def __init__(self, in_features: int, out_features: int, block_size: int = 128, bias: bool = True,
                  dtype: torch.dtype = torch.float16, device=None):
@@ -154,7 +158,8 @@ class TernaryLinear(nn.Module):
         tokens = x2.shape[0]
         dtype = self.alpha.dtype
         if tokens > self.gemv_max_tokens:
-            if self.fused_gemm and dtype != torch.float32 and self.in_features % 8 == 0:
+            if (self.fused_gemm and tokens <= self.fused_max_tokens and dtype != torch.float32
+                    and self.in_features % 8 == 0):
                 return self._forward_fused(x2.to(dtype)).reshape(*lead, self.out_features)
             out = torch.nn.functional.linear(x2.to(dtype), self._dequantize(), self.bias)
             return out.reshape(*lead, self.out_features)

@@ -35,6 +35,7 @@ def _layer(G, n, m, block, dtype, identity, bias, seed):
     layer = tq100.TernaryLinear(m, n, block_size=block, bias=bias, dtype=TDT[dtype], device=G.DEV)
     layer.set_quantized_params(G.dev(alpha), G.dev(mu), G.dev(T), G.dev(perm.astype(np.int64)), None if b is None else G.dev(b))
     layer.fused_gemm = True
+    layer.fused_max_tokens = 1 << 30
     return layer, (alpha, mu, T, perm, b)
 
 
@@ -80,11 +81,18 @@ def test_tl_gemm_tc_persistent_tiles_match_dense_path(G):
     assert (y.float() - y_dense.float()).abs().max().item() <= 4 * EPS["float16"] * want.abs().max().item()
 
 
-@pytest.mark.parametrize("tokens,dtype", [(256, "float16"), (512, "bfloat16"), (128, "float16")])
+@pytest.mark.parametrize("width", [128, 256, 512])
+def test_tl_gemm_tc_every_tile_width_vs_oracle(G, width, monkeypatch):
+    """The same ragged call (200 rows, K tail, 300 tokens, permuted, bias) forced through each tile width."""
+    monkeypatch.setenv("TQ_TL_GEMM_BN", str(width))
+    test_tl_gemm_tc_vs_oracle(G, 200, 1000, 128, 300, False, True, "float16")
+
+
+@pytest.mark.parametrize("tokens,dtype", [(256, "float16"), (1024, "bfloat16"), (128, "float16")])
 def test_tl_gemm_tc_more_tiles_than_sms(G, tokens, dtype):
-    """20480 x 1024: 160 row tiles > 148 SMs, so with one token tile per row tile some CTAs run two tiles of every
-    width (128-token tiles: 1 wave... 256 tokens -> 256-wide tiles, 512 tokens -> 512-wide tiles with the single
-    accumulator reused, 128 tokens -> 128-wide tiles)."""
+    """20480 x 1024: 160 row tiles > 148 SMs, so some CTAs run two tiles whatever the tile width the host picks
+    (256 tokens -> 256-wide tiles, 1024 tokens -> 512-wide tiles with the single accumulator reused, 128 tokens ->
+    128-wide tiles)."""
     layer, _ = _layer(G, 20480, 1024, 128, dtype, False, False, seed=31)
     gen = torch.Generator(device=G.DEV).manual_seed(tokens)
     x = torch.randn((tokens, 1024), generator=gen, device=G.DEV).to(TDT[dtype])
