@@ -63,14 +63,22 @@ template <typename HT> __device__ __forceinline__ HT tg_out(float v);
 template <> __device__ __forceinline__ __half tg_out<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ __nv_bfloat16 tg_out<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
-// the 16 positions of one code word (bit j: +1, bit 16+j: -1) -> 8 packed pairs of 16-bit weights (position 2i in
-// the low half of q[i]); h0/h1/h2 = bit patterns of w-, w0, w+
+// The 16 positions of one code word (bit j: +1, bit 16+j: -1) -> 8 packed pairs of 16-bit weights (position 2i in the
+// low half of q[i]); h0/h1/h2 = bit patterns of w-, w0, w+.  Byte-permute lookup instead of per-position selects: the
+// six bytes of (h0, h1, h2) sit in a register pair, and each output byte is picked by a selector nibble -- position j
+// needs the selector byte 0x10 + 0x22 u_j with u_j = 1 + P_j - N_j.  Four positions at a time: a nibble of a plane is
+// spread to one bit per byte by a multiply (copies at shifts 0/7/14/21 never overlap) and a mask, then
+// S = 0x32323232 + 0x22 spread(P) - 0x22 spread(N) holds the four selector bytes (no borrow: a position is never in
+// both planes) and two PRMTs emit the two pairs.  ~3.3 integer instructions per weight instead of ~4.5.
 __device__ __forceinline__ void tg_expand_word(uint32_t word, uint32_t h0, uint32_t h1, uint32_t h2, uint32_t (&q)[8]) {
+    const uint32_t A = h0 | (h1 << 16), B = h2;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const uint32_t lo = (word & (1u << (2 * i))) ? h2 : ((word & (1u << (16 + 2 * i))) ? h0 : h1);
-        const uint32_t hi = (word & (1u << (2 * i + 1))) ? h2 : ((word & (1u << (17 + 2 * i))) ? h0 : h1);
-        q[i] = lo | (hi << 16);
+    for (int g = 0; g < 4; ++g) {
+        const uint32_t pb = (((word >> (4 * g)) & 0xFu) * 0x00204081u) & 0x01010101u;
+        const uint32_t nb = (((word >> (16 + 4 * g)) & 0xFu) * 0x00204081u) & 0x01010101u;
+        const uint32_t S = 0x32323232u + 0x22u * pb - 0x22u * nb;
+        q[2 * g] = __byte_perm(A, B, S);
+        q[2 * g + 1] = __byte_perm(A, B, S >> 16);
     }
 }
 
