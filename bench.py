@@ -179,6 +179,56 @@ def workload_config(args, reference=False):
                 "(SSR statistics all-reduced per block)")}
 
 
+# ------------------------------------------------------------------------------------ N2 leg
+def packed_layer_leg(torch, tq100, dev):
+    n = m = 4096
+    gen = torch.Generator(device=dev).manual_seed(7)
+    T = torch.randint(-1, 2, (n, m), generator=gen, device=dev, dtype=torch.int8)
+    alpha = 0.01 + 0.02 * torch.rand((n, m // 128), generator=gen, device=dev)
+    mu = 0.004 * torch.randn((n, m // 128), generator=gen, device=dev)
+    perm = torch.randperm(m, generator=gen, device=dev)
+    code_bytes = n * (m // 16) * 4
+    copies = int(2.2 * 126e6 / code_bytes) + 1
+    layers = []
+    for _ in range(copies):
+        layer = tq100.TernaryLinear(m, n, bias=False, dtype=torch.float16, device=dev)
+        layer.set_quantized_params(alpha, mu, T, perm)
+        layers.append(layer)
+
+    def timed(fn, items, iters):
+        for it in items[:3]:
+            fn(it)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for i in range(iters):
+                fn(items[i % len(items)])
+        graph.replay()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        graph.replay()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters * 1e-3
+
+    x1 = torch.randn((1, m), generator=gen, device=dev).half()
+    t_dec = timed(lambda L: L(x1), layers, 2 * copies)
+    dec_bytes = code_bytes + 16 * n * (m // 128) + 2 * m + 4 * n
+    xs = torch.randn((512, m), generator=gen, device=dev).half()
+    out = {"layer": "4096x4096 fp16, block 128, random permutation",
+           "decode_1_token": {"us": t_dec * 1e6, "algorithmic_bytes": dec_bytes, "gbs": dec_bytes / t_dec / 1e9,
+                              "kernel": "tl_gemv_kernel", "copies": copies}}
+    for mode in ("fused", "dense"):
+        for L in layers[:3]:
+            L.fused_gemm = mode == "fused"
+        t = timed(lambda L: L(xs), layers[:3], 6)
+        out[f"tokens_512_{mode}"] = {"us": t * 1e6, "tflops": 2.0 * 512 * n * m / t / 1e12,
+                                     "kernel": "tl_gemm_tc_kernel" if mode == "fused" else "tl_expand_kernel + library GEMM"}
+    out["note"] = "SURVEY 8f N2 (TernaryLinear on 2-bit codes); secondary measurement, not part of `value`"
+    return out
+
+
 # ------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -193,6 +243,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-shared", action="store_true", help="skip the secondary shared-Hessian (N1) measurement")
+    ap.add_argument("--no-packed", action="store_true", help="skip the secondary packed-layer (N2) measurement")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
@@ -353,6 +404,17 @@ def main():
               "note": "same workload with LayerDriver(share_inputs=True): one Hessian + inverse per distinct calibration "
                       "input (SURVEY 8f N1); identical outputs; not the headline"}
 
+    # ---- SURVEY 8(f) N2, reported beside the headline: the packed inference layer on the codes (TernaryLinear):
+    # one 4096x4096 fp16 layer with a random permutation; decode call (1 token, tq_tl_gemv) over layer copies that
+    # total > 2x L2, and a 512-token call through tq_tl_gemm_tc vs dense weight + library GEMM.  Device-timed replay
+    # of a CUDA graph of the calls; never part of `value`.
+    n2 = None
+    if world == 1 and not args.no_packed:
+        try:
+            n2 = packed_layer_leg(torch, tq100, dev)
+        except Exception as exc:                                   # secondary measurement: never lose the headline line
+            n2 = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     # ---- e2e: same API from pinned host buffers, copies inside the timed region ------------------
     e2e = None
     if not args.no_e2e and world == 1:
@@ -429,6 +491,8 @@ def main():
             line["config"]["workload"] += f" [DEBUG: only {args.layers} of 32 layers]"
         if n1 is not None:
             line["n1_shared_inputs"] = n1
+        if n2 is not None:
+            line["n2_packed_layer"] = n2
         line["dtype_note"] = "fp32 arithmetic; fp16 activations enter the tensor cores exactly, fp32 accumulate"
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_arm()

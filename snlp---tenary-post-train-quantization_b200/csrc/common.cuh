@@ -48,6 +48,18 @@ extern std::atomic<long long> g_launches;
 
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device property of a kernel: `mask` (one static per kernel or
+// kernel family at the call site) remembers the devices it has been set on, so a process driving several GPUs sets it
+// on each of them once.
+static inline bool dyn_smem_pending(std::atomic<unsigned long long>& mask, int& dev) {
+    dev = 0;
+    cudaGetDevice(&dev);
+    return dev < 0 || dev >= 64 || !((mask.load(std::memory_order_relaxed) >> dev) & 1ull);
+}
+static inline void dyn_smem_done(std::atomic<unsigned long long>& mask, int dev) {
+    if (dev >= 0 && dev < 64) mask.fetch_or(1ull << dev, std::memory_order_relaxed);
+}
+
 int sm_count();
 
 // ---- device helpers --------------------------------------------------------------------------

@@ -341,15 +341,16 @@ extern "C" int tq_tl_gemm_tc(const uint32_t* codes, int64_t wpr, const float* wt
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(box >> 3) << 17) | ((uint32_t)(TG_BM >> 4) << 24);
     const int64_t tiles = (int64_t)p.row_tiles * p.tok_tiles;
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_devices{0};
+    int dev;
+    if (dyn_smem_pending(attr_devices, dev)) {
         TQ_CUDA(cudaFuncSetAttribute(tl_gemm_tc_kernel<__half, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
         TQ_CUDA(cudaFuncSetAttribute(tl_gemm_tc_kernel<__half, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
         TQ_CUDA(cudaFuncSetAttribute(tl_gemm_tc_kernel<__half, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
         TQ_CUDA(cudaFuncSetAttribute(tl_gemm_tc_kernel<__nv_bfloat16, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
         TQ_CUDA(cudaFuncSetAttribute(tl_gemm_tc_kernel<__nv_bfloat16, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
         TQ_CUDA(cudaFuncSetAttribute(tl_gemm_tc_kernel<__nv_bfloat16, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
-        attr_set = true;
+        dyn_smem_done(attr_devices, dev);
     }
     if (xdtype == TQ_F16) {
         if (bn == 512) tl_gemm_tc_kernel<__half, 512><<<grid, TG_THREADS, TG_SMEM, st>>>(map_x, p, idesc);

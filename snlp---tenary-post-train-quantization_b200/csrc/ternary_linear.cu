@@ -268,10 +268,11 @@ static int launch_gemv_mt(const uint32_t* codes, int64_t wpr, const float4* wt, 
                           int64_t block, const XT* x, int64_t ldx, int mt, const int32_t* perm, const float* bias, float* y,
                           int64_t ldy, cudaStream_t st) {
     constexpr int smem = tl_gemv_smem<MT>();
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<unsigned long long> attr_devices{0};
+    int dev;
+    if (dyn_smem_pending(attr_devices, dev)) {
         TQ_CUDA(cudaFuncSetAttribute(tl_gemv_kernel<XT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
+        dyn_smem_done(attr_devices, dev);
     }
     // block index of code word w = w / (block / 16): a shift, or a multiply-high by ceil(2^32 / wpb) (exact for
     // w * wpb < 2^32, i.e. any m < 2^31)

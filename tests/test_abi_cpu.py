@@ -43,6 +43,26 @@ def test_bad_arguments_return_status_and_message():
     assert b"tq_pack2b" in handle.tq_last_error_string()
 
 
+def test_packed_layer_argument_checks_need_no_gpu():
+    """tq_tl_* validate before touching CUDA: NULL pointers -> TQ_E_BADARG, a block size that lets a code word
+    straddle two scale blocks -> TQ_E_UNSUPPORTED, fp32 activations for the tensor-core GEMM -> TQ_E_UNSUPPORTED."""
+    import ctypes
+    handle = _lib.load()
+    assert handle.tq_tl_words_per_row(4096) == 256 and handle.tq_tl_words_per_row(17) == 2
+    assert handle.tq_tl_pack(None, 4, 16, None, None, 1, None) == -1
+    assert b"tq_tl_pack" in handle.tq_last_error_string()
+    buf = (ctypes.c_float * 64)()                       # host memory: only its address is inspected before the status
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert handle.tq_tl_gemv(p, 1, p, 4, 16, 24, p, 0, 16, 1, None, None, p, 4, None) == -2
+    assert b"multiple of 16" in handle.tq_last_error_string()
+    assert handle.tq_tl_gemv(p, 0, p, 4, 16, 16, p, 0, 16, 1, None, None, p, 4, None) == -1     # wpr < ceil(m/16)
+    assert handle.tq_tl_gemm_tc(p, 1, p, 4, 16, 16, p, 0, 16, 1, None, None, None, p, 4, None) == -2
+    assert b"f16 or bf16" in handle.tq_last_error_string()
+    assert handle.tq_tl_dequant(p, 1, p, 4, 16, 20, None, None, p, 0, 16, None) == -2
+    assert handle.tq_tl_wtab(p, p, 4, 1, 9, p, None) == -1
+    assert b"unknown dtype" in handle.tq_last_error_string()
+
+
 def test_no_cpu_fallback():
     q = tq100.AsymmetricTernaryQuantizer()
     with pytest.raises(RuntimeError, match="CUDA"):
