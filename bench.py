@@ -193,6 +193,7 @@ def packed_layer_leg(torch, tq100, dev):
     for _ in range(copies):
         layer = tq100.TernaryLinear(m, n, bias=False, dtype=torch.float16, device=dev)
         layer.set_quantized_params(alpha, mu, T, perm)
+        layer._prepared()             # derived buffers exist before any call is captured into a CUDA graph
         layers.append(layer)
 
     def timed(fn, items, iters):

@@ -100,6 +100,7 @@ class TernaryLinear(nn.Module):
         if bias is not None and self.bias is not None:
             self.bias.copy_(bias)
         self._invalidate()
+        self._prepared()              # build the weight table now: the first forward is then free of host syncs (graph capture)
 
     def _prepared(self):
         if self._derived is not None:
