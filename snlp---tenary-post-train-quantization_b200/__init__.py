@@ -35,4 +35,6 @@ from .model import (  # noqa: F401
     compute_compression_ratio,
 )
 
+from .main import PT2LLMQuantizer  # noqa: F401
+
 __version__ = "0.1.0"

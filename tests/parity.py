@@ -62,3 +62,25 @@ def assert_layer_parity(got, ref, block_size=128, same_perm_required=True, what=
         assert ea <= SCALE_RTOL, f"{what}: alpha rel err {ea:.3e} > {SCALE_RTOL}"
         assert em <= SCALE_RTOL, f"{what}: mu err (relative to alpha) {em:.3e} > {SCALE_RTOL}"
     return agree
+
+
+def assert_model_level_parity(name, got, ref):
+    """Layer 0 sees bit-identical inputs on both sides: north_star code agreement, scales to 5e-4.  Layer 1's inputs went through layer 0's
+    quantised weights, and the block sweep amplifies 1e-6 input differences into code flips at thresholds: the
+    REFERENCE AGAINST ITSELF (8 vs 1 MKL threads, same inputs) agrees on 0.9957 .. 0.9994 of layer 1's codes
+    (0.99997 .. 1.0 on layer 0), so layer 1 is held to that floor: >= 0.99 of the codes, scales of agreeing
+    (row, block) pairs within 1e-2."""
+    if name.startswith("layer_0."):
+        assert np.array_equal(got["perm"], ref["perm"]), name
+        assert code_agreement(got["T"], ref["T"]) >= CODE_AGREEMENT, name
+        mask = block_pairs_agree(got["T"], ref["T"], ref["perm"], 128)
+        # 5e-4 instead of the single-layer 1e-4: the AGA Gram is accumulated by a different GEMM (numpy here, the
+        # tcgen05 / FFMA SYRK on the GPU, MKL sgemm in the reference) and alpha of a few rows moves by ~1.2e-4
+        assert scale_rel_err(got["alpha"], ref["alpha"], mask) <= 5e-4, name
+        assert scale_rel_err(got["mu"], ref["mu"], mask, floor=np.abs(ref["alpha"].astype(np.float64))) <= 5e-4, name
+        return
+    assert np.array_equal(got["perm"], ref["perm"]), name
+    assert code_agreement(got["T"], ref["T"]) >= 0.99, name
+    mask = block_pairs_agree(got["T"], ref["T"], ref["perm"], 128)
+    assert mask.mean() > 0.5
+    assert scale_rel_err(got["alpha"], ref["alpha"], mask) <= 1e-2, name
