@@ -64,23 +64,37 @@ def assert_layer_parity(got, ref, block_size=128, same_perm_required=True, what=
     return agree
 
 
+def same_block_membership(perm_a, perm_b, block_size=128):
+    """True when every block of the two sweep orders holds the same SET of columns.  The order inside a block is
+    torch.topk's descending-similarity order (reorder.py:133-136); two similarities that differ by less than fp32 noise
+    may swap there, which changes nothing else: T is stored in original positions and alpha/mu are per-block sums."""
+    a, b = np.asarray(perm_a), np.asarray(perm_b)
+    if a.shape != b.shape:
+        return False
+    return all(np.array_equal(np.sort(a[k:k + block_size]), np.sort(b[k:k + block_size]))
+               for k in range(0, a.shape[0], block_size))
+
+
 def assert_model_level_parity(name, got, ref):
-    """Layer 0 sees bit-identical inputs on both sides: north_star code agreement, scales to 5e-4.  Layer 1's inputs went through layer 0's
-    quantised weights, and the block sweep amplifies 1e-6 input differences into code flips at thresholds: the
-    REFERENCE AGAINST ITSELF (8 vs 1 MKL threads, same inputs) agrees on 0.9957 .. 0.9994 of layer 1's codes
-    (0.99997 .. 1.0 on layer 0), so layer 1 is held to that floor: >= 0.99 of the codes, scales of agreeing
-    (row, block) pairs within 1e-2."""
-    if name.startswith("layer_0."):
-        assert np.array_equal(got["perm"], ref["perm"]), name
-        assert code_agreement(got["T"], ref["T"]) >= CODE_AGREEMENT, name
-        mask = block_pairs_agree(got["T"], ref["T"], ref["perm"], 128)
-        # 5e-4 instead of the single-layer 1e-4: the AGA Gram is accumulated by a different GEMM (numpy here, the
-        # tcgen05 / FFMA SYRK on the GPU, MKL sgemm in the reference) and alpha of a few rows moves by ~1.2e-4
-        assert scale_rel_err(got["alpha"], ref["alpha"], mask) <= 5e-4, name
-        assert scale_rel_err(got["mu"], ref["mu"], mask, floor=np.abs(ref["alpha"].astype(np.float64))) <= 5e-4, name
-        return
-    assert np.array_equal(got["perm"], ref["perm"]), name
-    assert code_agreement(got["T"], ref["T"]) >= 0.99, name
+    """Parity of one linear quantised inside a whole-model run (PT2LLMQuantizer.quantize) against the reference's run.
+
+    Layer 0 sees bit-identical inputs on both sides: same block membership, north_star code agreement, scales to 5e-4
+    (the single-layer bar is 1e-4; here the AGA Gram comes out of a different GEMM on each side -- numpy / the CUDA SYRK
+    / MKL sgemm -- and alpha of a few rows moves by ~1.2e-4).  Layer 1's inputs went through layer 0's quantised
+    weights, and the block sweep amplifies 1e-6 input differences into code flips at thresholds: the REFERENCE AGAINST
+    ITSELF (8 vs 1 MKL threads, same inputs) agrees on 0.9957 .. 0.9994 of layer 1's codes (0.99997 .. 1.0 on layer 0),
+    so layer 1 is held to that floor: >= 0.99 of the codes, scales of agreeing (row, block) pairs within 1e-2."""
+    first = name.startswith("layer_0.")
+    assert same_block_membership(got["perm"], ref["perm"]), f"{name}: block membership differs"
+    agree = code_agreement(got["T"], ref["T"])
+    assert agree >= (CODE_AGREEMENT if first else 0.99), f"{name}: code agreement {agree:.6f}"
     mask = block_pairs_agree(got["T"], ref["T"], ref["perm"], 128)
-    assert mask.mean() > 0.5
-    assert scale_rel_err(got["alpha"], ref["alpha"], mask) <= 1e-2, name
+    finite = np.isfinite(np.asarray(ref["alpha"], dtype=np.float64)) & (np.abs(np.asarray(ref["alpha"], dtype=np.float64)) < 1e3)
+    mask &= finite                           # rows the reference's AGA blew up (SURVEY Q9) carry ~1e14 scales on both sides
+    assert mask.mean() > 0.5, name
+    ea = scale_rel_err(got["alpha"], ref["alpha"], mask)
+    assert ea <= (5e-4 if first else 1e-2), f"{name}: alpha rel err {ea:.3e}"
+    if first:
+        em = scale_rel_err(got["mu"], ref["mu"], mask, floor=np.abs(np.asarray(ref["alpha"], dtype=np.float64)))
+        assert em <= 5e-4, f"{name}: mu err (relative to alpha) {em:.3e}"
+    return agree
