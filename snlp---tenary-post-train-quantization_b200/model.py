@@ -154,6 +154,8 @@ class TernaryLinear(nn.Module):
         _lib.require_cuda(x, "x")
         if x.shape[-1] != self.in_features:
             raise ValueError(f"expected (..., {self.in_features}) input, got {tuple(x.shape)}")
+        if x.device != self.codes.device:
+            raise RuntimeError(f"input is on {x.device} but the layer's codes are on {self.codes.device}")
         lead = x.shape[:-1]
         x2 = x.reshape(-1, self.in_features)
         tokens = x2.shape[0]
@@ -167,7 +169,7 @@ class TernaryLinear(nn.Module):
         wtab, perm32, bias32, _ = self._prepared()
         if x2.dtype not in (torch.float32, torch.float16, torch.bfloat16):
             x2 = x2.to(dtype)
-        if x2.stride(-1) != 1:
+        if x2.stride(-1) != 1 or (tokens > 1 and x2.stride(0) < self.in_features):
             x2 = x2.contiguous()
         y = torch.empty((tokens, self.out_features), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):

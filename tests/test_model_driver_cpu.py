@@ -6,7 +6,7 @@ The driver's two seams (how a per-linear quantiser is made, how a layer's quanti
 ORACLE here -- a test double for the CUDA path, legal only in tests -- so everything else is the product's own code:
 capture of the first layer's inputs, one accumulate forward + one advance forward per layer, streaming hooks, shared
 Hessians for linears fed the same tensor, parameter naming, weight overwrite.  The GPU twin of this test
-(tests/test_gpu_model_driver.py) runs the same comparison with the real kernels."""
+(tests/test_gpu_whole_model.py) runs the same comparison with the real kernels."""
 
 import os
 
