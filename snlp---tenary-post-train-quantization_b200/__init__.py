@@ -23,6 +23,9 @@ from .utils import (  # noqa: F401
     save_quantized_model,
     load_quantized_model,
     set_seed,
+    get_calibration_data,
+    prepare_calibration_inputs,
+    evaluate_perplexity,
 )
 from .model import (  # noqa: F401
     TernaryLinear,

@@ -21,7 +21,7 @@ calibration activations reach the hot path:
     ``main.py:313-335`` indexes ``T`` as if it were stored in sweep order although main.py:185 stores it in original
     positions (with SSR its reconstruction error is 1.37 instead of 0.32); for ``use_ssr=False`` the two agree.
 
-Dataset loading (``get_calibration_data``, utils.py:24-92) needs the network and is out of scope: pass the token
+Dataset loading (``utils.get_calibration_data``) needs the `datasets` cache or the network; without them pass the token
 tensors to ``quantize(calibration_samples=...)``.
 """
 
@@ -35,12 +35,12 @@ try:
     from . import gptq as _gptq
     from .model import find_linear_layers, get_llm_layers
     from .pipeline import LayerDriver
-    from .utils import set_seed
+    from .utils import set_seed, get_calibration_data as _get_calibration_data
 except ImportError:
     import gptq as _gptq
     from model import find_linear_layers, get_llm_layers
     from pipeline import LayerDriver
-    from utils import set_seed
+    from utils import set_seed, get_calibration_data as _get_calibration_data
 
 
 class _StopForward(Exception):
@@ -76,8 +76,17 @@ class PT2LLMQuantizer:
 
     # ------------------------------------------------------------------ main.py:90-100
     def get_calibration_data(self) -> List[torch.Tensor]:
-        raise RuntimeError("get_calibration_data() loads wikitext-2 through `datasets` (utils.py:24-92), which needs the "
-                           "network; pass the (1, seq_len) token tensors to quantize(calibration_samples=...)")
+        """main.py:90-100: wikitext-2 windows through utils.get_calibration_data.  Without the `datasets` cache or the
+        network this raises; pass the (1, seq_len) token tensors to quantize(calibration_samples=...) instead."""
+        if self.tokenizer is None:
+            raise RuntimeError("get_calibration_data() needs a tokenizer (and the `datasets` cache or the network); pass the "
+                               "token tensors to quantize(calibration_samples=...)")
+        try:
+            return _get_calibration_data(self.tokenizer, dataset_name="wikitext", dataset_config="wikitext-2-raw-v1",
+                                         num_samples=self.num_calibration_samples, seq_len=self.seq_len, seed=self.seed)
+        except Exception as exc:
+            raise RuntimeError("get_calibration_data() could not load wikitext-2 (it needs the `datasets` cache or the "
+                               "network); pass the token tensors to quantize(calibration_samples=...)") from exc
 
     # ------------------------------------------------------------------ main.py:102-230
     def quantize_layer(self, layer: nn.Linear, layer_name: str, calibration_activations: torch.Tensor):

@@ -94,3 +94,98 @@ def load_quantized_model(model: torch.nn.Module, load_path: str):
     checkpoint = torch.load(load_path, map_location="cpu")
     model.load_state_dict(checkpoint["model_state_dict"])
     return model, checkpoint.get("quantized_params", {})
+
+
+# ---------------------------------------------------------------------- calibration / evaluation plumbing
+def _load_text(dataset_name: str, dataset_config: str, split_kind: str, num_samples: int = 128) -> str:
+    """The text the reference concatenates (utils.py:45-62 for calibration, :156-164 for evaluation).  Needs the
+    `datasets` package and its cache / the network; callers without either pass `text=` or `tokens=` instead."""
+    try:
+        from datasets import load_dataset
+    except ImportError as exc:                                          # pragma: no cover
+        raise RuntimeError("the `datasets` package is not installed: pass text= or tokens=") from exc
+    train = split_kind == "train"
+    if dataset_name == "wikitext":
+        return "\n\n".join(load_dataset(dataset_name, dataset_config, split="train" if train else "test")["text"])
+    if dataset_name == "c4":
+        stream = load_dataset("allenai/c4", "en", split="train" if train else "validation", streaming=True)
+        return "\n\n".join(item["text"] for item in stream.take(num_samples * 10 if train else 1000))
+    if dataset_name == "ptb" and train:
+        return "\n\n".join(load_dataset("ptb_text_only", "penn_treebank", split="train")["sentence"])
+    raise ValueError(f"Unknown dataset: {dataset_name}")
+
+
+def get_calibration_data(tokenizer, dataset_name: str = "wikitext", dataset_config: str = "wikitext-2-raw-v1",
+                         num_samples: int = 128, seq_len: int = 2048, seed: int = 42, text: str = None,
+                         tokens: torch.Tensor = None):
+    """utils.py:24-72: `num_samples` windows of `seq_len` tokens at seeded random offsets of the tokenised corpus, each
+    (1, seq_len).  `text` / `tokens` (1-D ids) replace the dataset download; the sampling is the reference's
+    (set_seed, then random.randint(0, len - seq_len - 1) per sample)."""
+    import random
+    set_seed(seed)
+    if tokens is None:
+        if text is None:
+            text = _load_text(dataset_name, dataset_config, "train", num_samples)
+        tokens = tokenizer(text, return_tensors="pt")["input_ids"][0]
+    if len(tokens) < seq_len + 2:
+        raise ValueError(f"corpus has {len(tokens)} tokens, need more than seq_len + 1 = {seq_len + 1}")
+    samples = []
+    for _ in range(num_samples):
+        start = random.randint(0, len(tokens) - seq_len - 1)
+        samples.append(tokens[start:start + seq_len].unsqueeze(0))
+    return samples
+
+
+def prepare_calibration_inputs(model: torch.nn.Module, samples, device):
+    """utils.py:75-124: inputs of every nn.Linear over the samples, concatenated on the CPU.  Kept for API parity; the
+    quantisation path streams activations into GPTQ.add_batch instead of storing them (main.PT2LLMQuantizer)."""
+    activations, hooks = {}, []
+
+    def make_hook(name):
+        def hook(module, inp, out):
+            x = inp[0] if isinstance(inp, tuple) else inp
+            activations.setdefault(name, []).append(x.detach().cpu())
+        return hook
+
+    for name, module in model.named_modules():
+        if isinstance(module, torch.nn.Linear):
+            hooks.append(module.register_forward_hook(make_hook(name)))
+    model.eval()
+    try:
+        with torch.no_grad():
+            for sample in samples:
+                model(sample.to(device))
+    finally:
+        for h in hooks:
+            h.remove()
+    return {name: torch.cat(parts, dim=0) for name, parts in activations.items()}
+
+
+@torch.no_grad()
+def evaluate_perplexity(model: torch.nn.Module, tokenizer, dataset_name: str = "wikitext",
+                        dataset_config: str = "wikitext-2-raw-v1", seq_len: int = 2048, device=None, text: str = None,
+                        input_ids: torch.Tensor = None) -> float:
+    """utils.py:127-186: exp(mean NLL) over consecutive windows of `seq_len` tokens; the model is called as
+    model(input_chunk, labels=target_ids) and must return an object with `.loss` (HF causal LM).  `text` /
+    `input_ids` ((1, N) ids) replace the dataset download."""
+    if device is None:
+        device = next(model.parameters()).device
+    if input_ids is None:
+        if text is None:
+            text = _load_text(dataset_name, dataset_config, "eval")
+        input_ids = tokenizer(text, return_tensors="pt")["input_ids"]
+    input_ids = input_ids.to(device)
+    total = input_ids.size(1)
+    seq_len = min(seq_len, total)
+    nlls, prev_end = [], 0
+    for begin in range(0, total, seq_len):
+        end = min(begin + seq_len, total)
+        trg_len = end - prev_end
+        chunk = input_ids[:, begin:end]
+        target = chunk.clone()
+        target[:, :-trg_len] = -100
+        nlls.append(model(chunk, labels=target).loss * trg_len)
+        prev_end = end
+        if end >= total:
+            break
+    return torch.exp(torch.stack(nlls).sum() / prev_end).item()

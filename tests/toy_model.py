@@ -92,3 +92,40 @@ def build(seed=7, **kw):
 def samples(num=16, seq=64, vocab=64, seed=11):
     gen = torch.Generator().manual_seed(seed)
     return [torch.randint(0, vocab, (1, seq), generator=gen) for _ in range(num)]
+
+
+class CausalLMOutput:
+    def __init__(self, loss, logits):
+        self.loss, self.logits = loss, logits
+
+
+class ToyCausalLM(nn.Module):
+    """HF-style call signature over ToyLM: model(input_ids, labels=...) -> object with .loss (labels shifted by one,
+    -100 ignored, mean over the rest), which is what utils.evaluate_perplexity relies on (utils.py:176-177)."""
+
+    def __init__(self, lm):
+        super().__init__()
+        self.lm = lm
+
+    def forward(self, input_ids, labels=None):
+        logits = self.lm(input_ids)
+        loss = None
+        if labels is not None:
+            loss = torch.nn.functional.cross_entropy(logits[:, :-1].reshape(-1, logits.shape[-1]), labels[:, 1:].reshape(-1),
+                                                     ignore_index=-100)
+        return CausalLMOutput(loss, logits)
+
+
+class CharTokenizer:
+    """tokenizer(text, return_tensors='pt')['input_ids'] -> (1, len) ids: byte value modulo the vocabulary."""
+
+    def __init__(self, vocab=64):
+        self.vocab = vocab
+
+    def __call__(self, text, return_tensors="pt"):
+        return {"input_ids": torch.tensor([[b % self.vocab for b in text.encode()]], dtype=torch.long)}
+
+
+def corpus(n_chars=3000, seed=5):
+    gen = torch.Generator().manual_seed(seed)
+    return "".join(chr(97 + int(v)) for v in torch.randint(0, 26, (n_chars,), generator=gen))
