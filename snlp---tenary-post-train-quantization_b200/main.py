@@ -33,12 +33,12 @@ import torch.nn as nn
 
 try:
     from . import gptq as _gptq
-    from .model import find_linear_layers, get_llm_layers
+    from .model import find_linear_layers, get_llm_layers, replace_linear_with_ternary as _replace_linear_with_ternary
     from .pipeline import LayerDriver
     from .utils import set_seed, get_calibration_data as _get_calibration_data
 except ImportError:
     import gptq as _gptq
-    from model import find_linear_layers, get_llm_layers
+    from model import find_linear_layers, get_llm_layers, replace_linear_with_ternary as _replace_linear_with_ternary
     from pipeline import LayerDriver
     from utils import set_seed, get_calibration_data as _get_calibration_data
 
@@ -195,6 +195,22 @@ class PT2LLMQuantizer:
         driver = LayerDriver(gs[0].device, block_size=self.block_size, percdamp=self.percdamp, num_streams=self.num_streams)
         # AGA on the raw-activation Gram, as main.py:177-180 feeds it
         return driver.run_chains(gs, use_ssr=self.use_ssr, aga="activations")
+
+    def replace_with_ternary(self, dtype: Optional[torch.dtype] = None) -> nn.Module:
+        """After quantize(): swap every quantised nn.Linear of the model for a TernaryLinear on its 2-bit codes
+        (model.replace_linear_with_ternary, model.py:174-225).  The keys of ``quantized_params`` are the reference's
+        ``layer_{i}.{name}`` (main.py:290), so each transformer layer is handed its own sub-dictionary.  ``dtype`` casts
+        alpha / mu (and with them the layer) -- the reference's default layer dtype is fp16 (model.py:34)."""
+        layers = get_llm_layers(self.model, self.model_type)
+        per_layer: Dict[int, Dict[str, Dict[str, torch.Tensor]]] = {}
+        for key, params in self.quantized_params.items():
+            head, name = key.split(".", 1)
+            if dtype is not None:
+                params = dict(params, alpha=params["alpha"].to(dtype), mu=params["mu"].to(dtype))
+            per_layer.setdefault(int(head[len("layer_"):]), {})[name] = params
+        for idx, group in per_layer.items():
+            _replace_linear_with_ternary(layers[idx], group, block_size=self.block_size)
+        return self.model
 
     # ------------------------------------------------------------------ main.py:313-335
     def _dequantize_weight(self, params: Dict[str, torch.Tensor]) -> torch.Tensor:

@@ -138,3 +138,23 @@ def test_dequantize_weight_and_calibration_stub():
     np.testing.assert_array_equal(W, want)
     with pytest.raises(RuntimeError, match="network"):
         pq.quantize()
+
+
+def test_replace_with_ternary_routes_each_layer_its_own_parameters(monkeypatch):
+    """Host routing only (the layer swap itself runs on the GPU: tests/test_gpu_ternary_linear.py)."""
+    import tq100
+    calls = []
+    monkeypatch.setattr(tq100.main, "_replace_linear_with_ternary",
+                        lambda module, params, block_size: calls.append((module, params, block_size)))
+    model = toy_model.build()
+    pq = tq100.PT2LLMQuantizer(model, None, device="cpu")
+    z = torch.zeros(1)
+    pq.quantized_params = {"layer_0.self_attn.q_proj": {"alpha": z, "mu": z, "T": z, "perm": z},
+                           "layer_1.mlp.down_proj": {"alpha": z, "mu": z, "T": z, "perm": z},
+                           "layer_1.mlp.up_proj": {"alpha": z, "mu": z, "T": z, "perm": z}}
+    assert pq.replace_with_ternary(dtype=torch.float16) is model
+    assert [c[0] for c in calls] == [model.model.layers[0], model.model.layers[1]] and all(c[2] == 128 for c in calls)
+    assert sorted(calls[1][1]) == ["mlp.down_proj", "mlp.up_proj"] and sorted(calls[0][1]) == ["self_attn.q_proj"]
+    assert calls[0][1]["self_attn.q_proj"]["alpha"].dtype == torch.float16
+    assert pq.quantized_params["layer_0.self_attn.q_proj"]["alpha"].dtype == torch.float32       # stored copy untouched
+
