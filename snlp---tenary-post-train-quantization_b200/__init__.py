@@ -1,5 +1,6 @@
-"""B200-native ternary GPTQ hot path (PT2-LLM): the reference's gptq / quantizer / reorder / pack API
-over hand-written sm_100a CUDA kernels behind a C ABI (include/tq100.h, libtq100.so)."""
+"""B200-native ternary GPTQ hot path (PT2-LLM): the reference's gptq / quantizer / reorder / pack API, its ternary
+inference layer (model.py) and its whole-model driver (main.py) over hand-written sm_100a CUDA kernels behind a C ABI
+(include/tq100.h, libtq100.so)."""
 
 from . import _lib  # noqa: F401
 from .quantizer import (  # noqa: F401
