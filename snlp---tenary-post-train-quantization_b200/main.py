@@ -21,6 +21,10 @@ calibration activations reach the hot path:
     ``main.py:313-335`` indexes ``T`` as if it were stored in sweep order although main.py:185 stores it in original
     positions (with SSR its reconstruction error is 1.37 instead of 0.32); for ``use_ssr=False`` the two agree.
 
+Under ``torchrun`` pass ``shard=sharded.ShardContext(rank, world, device)``: the calibration samples are dealt to the ranks
+(each rank runs the forwards of its own), the Hessians are all-reduced per layer, the linears are dealt to the ranks by
+chain cost and their results broadcast, so every rank ends with the same quantised model and parameters.
+
 Dataset loading (``utils.get_calibration_data``) needs the `datasets` cache or the network; without them pass the token
 tensors to ``quantize(calibration_samples=...)``.
 """
@@ -53,7 +57,7 @@ class PT2LLMQuantizer:
     def __init__(self, model: nn.Module, tokenizer, model_type: str = "llama", block_size: int = 128,
                  num_calibration_samples: int = 128, seq_len: int = 2048, use_ssr: bool = True, percdamp: float = 0.01,
                  seed: int = 42, device: str = "cuda", share_inputs: bool = True, num_streams: int = 4,
-                 gptq_factory: Optional[Callable] = None, chain_runner: Optional[Callable] = None):
+                 gptq_factory: Optional[Callable] = None, chain_runner: Optional[Callable] = None, shard=None):
         self.model = model
         self.tokenizer = tokenizer
         self.model_type = model_type
@@ -70,6 +74,10 @@ class PT2LLMQuantizer:
         self._gptq_factory = gptq_factory or (lambda layer, hessian: _gptq.GPTQ(layer, block_size=self.block_size,
                                                                                  percdamp=self.percdamp, hessian=hessian))
         self._chain_runner = chain_runner
+        # multi-GPU: a sharded.ShardContext under torchrun.  Every rank holds the model, runs the forwards of
+        # ITS calibration samples and accumulates local Hessians; per layer the Hessians are all-reduced, the linears
+        # are dealt to the ranks by chain cost, each owner quantises its linears and broadcasts their results.
+        self.shard = shard if shard is not None and getattr(shard, "world", 1) > 1 else None
         set_seed(seed)
         self.quantized_params: Dict[str, Dict[str, torch.Tensor]] = {}
         self.layer_forwards = 0              # transformer-layer forwards executed by quantize() (2 per layer and sample)
@@ -101,18 +109,26 @@ class PT2LLMQuantizer:
             calibration_samples = self.get_calibration_data()
         layers = get_llm_layers(self.model, self.model_type)
         self.model.eval()
+        if self.shard is not None:
+            calibration_samples = [calibration_samples[i] for i in self.shard.my_samples(len(calibration_samples))]
         inputs = self._capture_first_layer_inputs(layers[0], calibration_samples)
         for layer_idx, layer in enumerate(layers):
             linear_layers = find_linear_layers(layer)
             quantizers = self._accumulate(layer, linear_layers, inputs)
             names = [n for n in linear_layers if n in quantizers]
-            self._run_chains([quantizers[n] for n in names])
-            for name in names:
+            owners = self._reduce_and_deal(quantizers, names)
+            rank = self.shard.rank if self.shard is not None else 0
+            self._run_chains([quantizers[n] for n, o in zip(names, owners) if o == rank])
+            for name, owner in zip(names, owners):
                 g, linear = quantizers[name], linear_layers[name]
-                params = {"alpha": g.alpha.float().cpu(), "mu": g.mu.float().cpu(), "T": g.T_int8.cpu(),
-                          "perm": g.perm.cpu()}                                              # main.py:225-230
-                self.quantized_params[f"layer_{layer_idx}.{name}"] = params
-                W_quant = g.get_quantized_weight()                                           # main.py:298-299
+                if owner == rank:
+                    res = (g.alpha.float(), g.mu.float(), g.T_int8, g.perm,
+                           g.get_quantized_weight().to(linear.weight.dtype))                 # main.py:298-299
+                else:
+                    res = None
+                alpha, mu, T8, perm, W_quant = self._publish(res, owner, g, linear)
+                self.quantized_params[f"layer_{layer_idx}.{name}"] = {"alpha": alpha.cpu(), "mu": mu.cpu(), "T": T8.cpu(),
+                                                                      "perm": perm.cpu()}    # main.py:225-230
                 linear.weight.data = W_quant.to(linear.weight.device, linear.weight.dtype)
             del quantizers
             if layer_idx + 1 < len(layers):
@@ -187,11 +203,56 @@ class PT2LLMQuantizer:
                 h.remove()
         return quantizers
 
+    def _reduce_and_deal(self, quantizers, names):
+        """Single process: every linear is rank 0's.  Sharded: all-reduce every distinct Hessian and its token count
+        (the NCCL all-reduce of H over NVLink of SURVEY 8e; identical on every rank afterwards), then deal the linears
+        to the ranks by estimated chain duration (sharded.deal_linears: deterministic, same answer on every rank)."""
+        if self.shard is None:
+            return [0] * len(names)
+        import torch.distributed as dist
+        try:
+            from .sharded import deal_linears
+        except ImportError:
+            from sharded import deal_linears
+        seen = set()
+        for name in names:
+            st = quantizers[name].state
+            if id(st) in seen:
+                continue
+            seen.add(id(st))
+            H = st.H if torch.is_tensor(st.H) else torch.from_numpy(st.H)       # (numpy only in the host-logic tests)
+            dist.all_reduce(H, op=dist.ReduceOp.SUM, group=self.shard.group)
+            count = torch.tensor([st.nsamples], dtype=torch.int64, device=H.device)
+            dist.all_reduce(count, op=dist.ReduceOp.SUM, group=self.shard.group)
+            st.nsamples = int(count.item())
+            if hasattr(st, "_cache"):
+                st._cache.clear()
+        return deal_linears([(quantizers[n].rows, quantizers[n].columns) for n in names], self.shard.world)
+
+    def _publish(self, res, owner, g, linear):
+        """Owner -> everyone: (alpha, mu, T int8, perm, dequantised weight) of one linear."""
+        if self.shard is None:
+            return res
+        import torch.distributed as dist
+        n, m = g.rows, g.columns
+        nb = (m + self.block_size - 1) // self.block_size
+        dev = linear.weight.device
+        if res is None:
+            res = (torch.empty((n, nb), dtype=torch.float32, device=dev), torch.empty((n, nb), dtype=torch.float32, device=dev),
+                   torch.empty((n, m), dtype=torch.int8, device=dev), torch.empty(m, dtype=torch.int64, device=dev),
+                   torch.empty((n, m), dtype=linear.weight.dtype, device=dev))
+        out = []
+        for t in res:
+            t = t.to(dev).contiguous()
+            dist.broadcast(t, src=owner, group=self.shard.group)
+            out.append(t)
+        return tuple(out)
+
     def _run_chains(self, gs):
-        if self._chain_runner is not None:
-            return self._chain_runner(gs, self.use_ssr)
         if not gs:
             return gs
+        if self._chain_runner is not None:
+            return self._chain_runner(gs, self.use_ssr)
         driver = LayerDriver(gs[0].device, block_size=self.block_size, percdamp=self.percdamp, num_streams=self.num_streams)
         # AGA on the raw-activation Gram, as main.py:177-180 feeds it
         return driver.run_chains(gs, use_ssr=self.use_ssr, aga="activations")
