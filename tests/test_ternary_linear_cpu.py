@@ -9,7 +9,6 @@ import pytest
 import torch
 import torch.nn as nn
 
-import oracle
 from oracle import ternary_linear as otl
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
