@@ -19,3 +19,15 @@ def test_sharded_layer_matches_single_gpu():
            "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(HERE, "mgpu_worker.py")]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0 and "MGPU_OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")
+@pytest.mark.skipif(os.environ.get("TQ_TEST_SHARDED_MODEL") != "1",
+                    reason="sharded whole-model driver: verified with gloo on CPU (tests/test_model_driver_sharded_cpu.py); "
+                           "its NCCL run has not been on a GPU box yet -- set TQ_TEST_SHARDED_MODEL=1 to run it")
+def test_sharded_whole_model_matches_reference():
+    n = min(torch.cuda.device_count(), 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", "29613", os.path.join(HERE, "mgpu_model_worker.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "MGPU_MODEL_OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
