@@ -160,6 +160,8 @@ class TernaryLinear(nn.Module):
         x2 = x.reshape(-1, self.in_features)
         tokens = x2.shape[0]
         dtype = self.alpha.dtype
+        if tokens == 0:
+            return torch.empty((*lead, self.out_features), dtype=dtype, device=x.device)
         if tokens > self.gemv_max_tokens:
             if (self.fused_gemm and tokens <= self.fused_max_tokens and dtype != torch.float32
                     and self.in_features % 8 == 0):
