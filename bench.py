@@ -405,17 +405,6 @@ def main():
               "note": "same workload with LayerDriver(share_inputs=True): one Hessian + inverse per distinct calibration "
                       "input (SURVEY 8f N1); identical outputs; not the headline"}
 
-    # ---- SURVEY 8(f) N2, reported beside the headline: the packed inference layer on the codes (TernaryLinear):
-    # one 4096x4096 fp16 layer with a random permutation; decode call (1 token, tq_tl_gemv) over layer copies that
-    # total > 2x L2, and a 512-token call through tq_tl_gemm_tc vs dense weight + library GEMM.  Device-timed replay
-    # of a CUDA graph of the calls; never part of `value`.
-    n2 = None
-    if world == 1 and not args.no_packed:
-        try:
-            n2 = packed_layer_leg(torch, tq100, dev)
-        except Exception as exc:                                   # secondary measurement: never lose the headline line
-            n2 = {"error": f"{type(exc).__name__}: {exc}"[:300]}
-
     # ---- e2e: same API from pinned host buffers, copies inside the timed region ------------------
     e2e = None
     if not args.no_e2e and world == 1:
@@ -482,6 +471,18 @@ def main():
         t = torch.tensor([e2e["value"]], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e["value"] = float(t.item())
+    # ---- SURVEY 8(f) N2, reported beside the headline: the packed inference layer on the codes (TernaryLinear):
+    # one 4096x4096 fp16 layer with a random permutation; decode call (1 token, tq_tl_gemv) over layer copies that
+    # total > 2x L2, and a 512-token call through tq_tl_gemm_tc vs dense weight + library GEMM.  Device-timed replay
+    # of a CUDA graph of the calls; never part of `value`;
+    # last, so that nothing it does can disturb the measurements above.
+    n2 = None
+    if world == 1 and not args.no_packed:
+        try:
+            n2 = packed_layer_leg(torch, tq100, dev)
+        except Exception as exc:                                   # secondary measurement: never lose the headline line
+            n2 = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     if rank == 0:
         line = {"metric": "LLaMA-2-7B ternary PTQ wall-time", "value": value, "unit": "s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
