@@ -46,6 +46,7 @@ class HessianState:
         self._upper_only = False      # the tcgen05 path fills only tiles touching the upper triangle
         self._cache = {}
         self._cache_events = {}
+        self._full_event = None       # (event, stream) of the last symmetrisation, for readers on other streams
 
     def add_batch(self, inp: torch.Tensor):
         lib = _lib.load()
@@ -66,17 +67,25 @@ class HessianState:
                                             _lib.stream()), "tq_hessian_accum")
         x.record_stream(torch.cuda.current_stream(self.device))
         self._upper_only = True
+        self._full_event = None
         self._cache.clear()
         self.nsamples += nt                                     # gptq.py:76
 
     def full(self) -> torch.Tensor:
-        """H as a full symmetric matrix (mirrors the upper triangle on first read)."""
+        """H as a full symmetric matrix (mirrors the upper triangle on first read).  Linears sharing this state may read
+        it from other streams than the one the mirroring kernel ran on: those wait for its event."""
+        cur = torch.cuda.current_stream(self.device)
         if self._upper_only:
             lib = _lib.load()
             with torch.cuda.device(self.device):
                 _lib.check(lib.tq_symmetrize(_lib.ptr(self.H), self.columns, self.columns, _lib.stream()),
                            "tq_symmetrize")
             self._upper_only = False
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._full_event = (ev, cur)
+        elif self._full_event is not None and self._full_event[1] != cur:
+            cur.wait_event(self._full_event[0])
         return self.H
 
     def damped(self, percdamp: float) -> torch.Tensor:
@@ -202,6 +211,10 @@ class GPTQ:
         dev = self.device
         nb = (m + b - 1) // b
 
+        if aga == "activations":
+            # the AGA Gram reads H[blk, blk] on both sides of the diagonal: mirror the tcgen05 SYRK's upper tiles BEFORE the
+            # inverse is enqueued (its cache event then also covers the mirroring for linears sharing this Hessian)
+            self.state.full()
         Hd, Hinv, info = self.state.damped_inverse(self.percdamp)
         static_perm = None
         order_code = {"ssr": _lib.ORDER_SSR, "sequential": _lib.ORDER_SEQUENTIAL, "actorder": _lib.ORDER_STATIC}[order]
@@ -226,8 +239,6 @@ class GPTQ:
                 t.record_stream(torch.cuda.current_stream(dev))
             return alpha, mu, T8, perm
 
-        if aga == "activations":
-            self.state.full()            # the AGA Gram reads H[blk, blk] on both sides of the diagonal
         self._pending = (run, Hd, info, run(Hinv), torch.cuda.current_stream(dev))
 
     @torch.no_grad()

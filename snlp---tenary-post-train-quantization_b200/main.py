@@ -29,6 +29,7 @@ Dataset loading (``utils.get_calibration_data``) needs the `datasets` cache or t
 tensors to ``quantize(calibration_samples=...)``.
 """
 
+import inspect
 import time
 from typing import Callable, Dict, List, Optional
 
@@ -49,6 +50,10 @@ except ImportError:
 
 class _StopForward(Exception):
     pass
+
+
+# decoder-layer keyword arguments that carry (or switch on) a KV cache in Hugging Face models
+_CACHE_KWARGS = ("past_key_value", "past_key_values", "use_cache", "layer_past")
 
 
 class PT2LLMQuantizer:
@@ -110,6 +115,9 @@ class PT2LLMQuantizer:
         layers = get_llm_layers(self.model, self.model_type)
         self.model.eval()
         if self.shard is not None:
+            if len(calibration_samples) < self.shard.world:
+                # a rank without samples would skip the forwards (and the collectives that follow them) and hang the rest
+                raise ValueError(f"{len(calibration_samples)} calibration samples cannot be dealt to {self.shard.world} ranks")
             calibration_samples = [calibration_samples[i] for i in self.shard.my_samples(len(calibration_samples))]
         inputs = self._capture_first_layer_inputs(layers[0], calibration_samples)
         for layer_idx, layer in enumerate(layers):
@@ -141,15 +149,31 @@ class PT2LLMQuantizer:
         captured = []
 
         def pre_hook(module, args, kwargs):
-            captured.append((tuple(a.detach() if torch.is_tensor(a) else a for a in args),
-                             {k: (v.detach() if torch.is_tensor(v) else v) for k, v in kwargs.items()}))
+            # Every layer is later run TWICE on these kwargs (original weights, then quantised weights).  A live KV cache
+            # among them would be appended to by the first pass and attended to by the second, so the cache and the flag
+            # that enables it are dropped: the layers run cache-free, like a fresh whole-model forward of the reference
+            # (main.py:278-282).
+            kept = {}
+            for k, v in kwargs.items():
+                if k in _CACHE_KWARGS:
+                    kept[k] = False if k == "use_cache" else None
+                else:
+                    kept[k] = v.detach() if torch.is_tensor(v) else v
+            captured.append((tuple(a.detach() if torch.is_tensor(a) else a for a in args), kept))
             raise _StopForward()
 
+        # ask the model not to build a KV cache at all when its forward knows the flag (Hugging Face causal LMs do)
+        try:
+            params = inspect.signature(self.model.forward).parameters
+            takes_flag = "use_cache" in params or any(p.kind is inspect.Parameter.VAR_KEYWORD for p in params.values())
+        except (TypeError, ValueError):
+            takes_flag = False
+        no_cache = {"use_cache": False} if takes_flag else {}
         handle = first_layer.register_forward_pre_hook(pre_hook, with_kwargs=True)
         try:
             for sample in samples:
                 try:
-                    self.model(sample.to(self.device))
+                    self.model(sample.to(self.device), **no_cache)
                 except _StopForward:
                     pass
         finally:

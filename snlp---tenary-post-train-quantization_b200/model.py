@@ -35,8 +35,48 @@ except ImportError:
     import _lib
 
 
+def codes_from_T(T: torch.Tensor, perm: torch.Tensor) -> torch.Tensor:
+    """Checkpoint interchange (host glue, any device): the reference's int8 ``T`` buffer (model.py:43; original column
+    positions) -> the TL2 code words of include/tq100.h: word w of a row holds sweep positions 16w..16w+15, bit j set
+    where T = +1, bit 16+j where T = -1.  Bit-identical to ``tq_tl_pack`` (tests/test_gpu_ternary_linear.py)."""
+    n, m = T.shape
+    Ts = T.to(torch.int64).index_select(1, perm.to(device=T.device, dtype=torch.long))
+    pad = (-m) % 16
+    if pad:
+        Ts = torch.nn.functional.pad(Ts, (0, pad))
+    Ts = Ts.view(n, -1, 16)
+    w = torch.ones(16, dtype=torch.int64, device=T.device) << torch.arange(16, device=T.device)
+    word = ((Ts == 1).to(torch.int64) * w).sum(-1) | (((Ts == -1).to(torch.int64) * w).sum(-1) << 16)
+    return torch.where(word >= 2 ** 31, word - 2 ** 32, word).to(torch.int32)
+
+
+def T_from_codes(codes: torch.Tensor, perm: torch.Tensor, m: int) -> torch.Tensor:
+    """Inverse of codes_from_T: int8 (n, m) in original column positions."""
+    n = codes.shape[0]
+    word = codes.to(torch.int64) & 0xFFFFFFFF
+    j = torch.arange(16, device=codes.device)
+    plus = (word.unsqueeze(-1) >> j) & 1
+    minus = (word.unsqueeze(-1) >> (j + 16)) & 1
+    Ts = (plus - minus).view(n, -1)[:, :m].to(torch.int8)
+    T = torch.empty_like(Ts)
+    T[:, perm.to(device=codes.device, dtype=torch.long)] = Ts
+    return T
+
+
+def _after_load(module, incompatible):
+    module._invalidate()
+
+
 class TernaryLinear(nn.Module):
-    """model.py:17-127 on packed codes."""
+    """model.py:17-127 on packed codes.
+
+    Checkpoints: the state dict holds ``codes`` (2-bit planes) where the reference's holds an int8 ``T``
+    (model.py:43).  Loading accepts either: a reference-produced ``<prefix>T`` is packed on the way in
+    (``_load_from_state_dict``).  ``TernaryLinear.export_reference_T = True`` makes ``state_dict()`` also carry
+    ``<prefix>T`` so the reference's ``load_quantized_model`` (utils.py:299-304, ``strict=False`` for the extra
+    ``codes`` / ``inv_perm`` keys) can read checkpoints written here."""
+
+    export_reference_T = False
 
     gemv_max_tokens = 16
     # many-token path of fp16/bf16 layers: tq_tl_gemm_tc up to fused_max_tokens rows, dense weight + library GEMM beyond
@@ -68,7 +108,30 @@ class TernaryLinear(nn.Module):
         else:
             self.bias = None
         self._derived = None          # (wtab f32 [n, nb, 4], perm / inv_perm int32 or None, bias f32 or None), rebuilt lazily
-        self.register_load_state_dict_post_hook(lambda module, incompatible: module._invalidate())
+        self.register_load_state_dict_post_hook(_after_load)      # a module-level function: the layer stays picklable
+        self._register_state_dict_hook(TernaryLinear._export_T)
+
+    @staticmethod
+    def _export_T(module, state_dict, prefix, local_metadata):
+        if module.export_reference_T:
+            state_dict[prefix + "T"] = T_from_codes(module.codes, module.perm, module.in_features)
+        return state_dict
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        """Accept the reference's checkpoint layout (int8 ``T`` in original positions + ``perm``, model.py:43-47) next to
+        this layer's own (``codes``): T is packed into code words before the regular loading runs."""
+        tkey, ckey = prefix + "T", prefix + "codes"
+        if tkey in state_dict:
+            T = state_dict.pop(tkey)
+            if ckey not in state_dict:
+                perm = state_dict.get(prefix + "perm", self.perm)
+                if tuple(T.shape) != (self.out_features, self.in_features):
+                    error_msgs.append(f"size mismatch for {tkey}: {tuple(T.shape)} vs {(self.out_features, self.in_features)}")
+                else:
+                    state_dict[ckey] = codes_from_T(T, perm)
+                    if prefix + "inv_perm" not in state_dict:
+                        state_dict[prefix + "inv_perm"] = torch.argsort(perm.long())
+        super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
 
     # ------------------------------------------------------------------ parameters
     def _invalidate(self):

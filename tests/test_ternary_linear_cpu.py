@@ -155,3 +155,50 @@ def test_model_walkers():
     assert tq100.compute_bits_per_weight(lm) == 16.0
     assert tq100.compute_compression_ratio(4.0, 1.0) == 4.0
     assert tq100.compute_model_size(lm) > 0
+
+
+# ---------------------------------------------------------------------- checkpoint interchange with the reference
+def test_reference_checkpoint_layout_loads_and_exports(tmp_path):
+    """The reference's TernaryLinear keeps an int8 buffer ``T`` in original positions (model.py:43) and its
+    save_quantized_model / load_quantized_model (utils.py:288-304) round-trip the state dict.  A state dict in that
+    layout must load into this layer (packed on the way in, bit-identical to the oracle's pack_layer), and
+    ``export_reference_T`` must write it back out."""
+    import pickle
+    import tq100
+    from tq100 import model as tmodel
+    rng = np.random.default_rng(5)
+    n, m = 24, 200                                   # ragged: 200 = 12 words + 8 positions
+    T = rng.integers(-1, 2, size=(n, m)).astype(np.int8)
+    perm = rng.permutation(m)
+    words = otl.pack_layer(T, perm)
+    got = tmodel.codes_from_T(torch.from_numpy(T), torch.from_numpy(perm))
+    np.testing.assert_array_equal(got.numpy().view(np.uint32), words)
+    np.testing.assert_array_equal(tmodel.T_from_codes(got, torch.from_numpy(perm), m).numpy(), T)
+
+    ref_state = {"T": torch.from_numpy(T), "alpha": torch.rand(n, 2).half(), "mu": torch.rand(n, 2).half(),
+                 "perm": torch.from_numpy(perm)}                       # the reference's buffers, bias=False
+    layer = tq100.TernaryLinear(m, n, block_size=128, bias=False, dtype=torch.float16)
+    missing = layer.load_state_dict(ref_state, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    np.testing.assert_array_equal(layer.codes.numpy().view(np.uint32), words)
+    assert torch.equal(layer.inv_perm, torch.argsort(torch.from_numpy(perm)))
+    assert torch.equal(layer.alpha, ref_state["alpha"])
+
+    # through the one-file checkpoint of utils.save_quantized_model / load_quantized_model
+    holder = nn.Sequential(layer)
+    path = str(tmp_path / "q.pt")
+    tq100.TernaryLinear.export_reference_T = True
+    try:
+        tq100.save_quantized_model(holder, path, {"0": {"perm": torch.from_numpy(perm)}})
+        saved = torch.load(path, map_location="cpu")["model_state_dict"]
+        assert torch.equal(saved["0.T"], torch.from_numpy(T)) and saved["0.T"].dtype == torch.int8
+    finally:
+        tq100.TernaryLinear.export_reference_T = False
+    fresh = nn.Sequential(tq100.TernaryLinear(m, n, block_size=128, bias=False, dtype=torch.float16))
+    _, params = tq100.load_quantized_model(fresh, path)
+    assert torch.equal(fresh[0].codes, layer.codes) and "0" in params
+    assert "0.T" not in fresh.state_dict()
+
+    # whole-module pickle (torch.save(model)) works: no lambda hooks on the layer
+    clone = pickle.loads(pickle.dumps(layer))
+    assert torch.equal(clone.codes, layer.codes)
