@@ -49,7 +49,8 @@ def damped_inverse(Hraw, nsamples, percdamp=0.01):
         if info2 == 0:
             inv = np.tril(inv) + np.tril(inv, -1).T
             return H, np.ascontiguousarray(inv, dtype=dt)
-    return H, np.linalg.pinv(H).astype(dt)
+    # torch.linalg.pinv's default cutoff (gptq.py:106): singular values below max(m, n) * eps * sigma_max are dropped
+    return H, np.linalg.pinv(H, rcond=max(H.shape) * np.finfo(dt).eps).astype(dt)
 
 
 def quantize_layer(W, Hraw, nsamples, block_size=128, percdamp=0.01, order="ssr",

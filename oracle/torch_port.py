@@ -22,9 +22,11 @@ def _round(W, alpha, mu):
     return (Z > 0.5).to(W.dtype) - (Z < -0.5).to(W.dtype)           # quantizer.py:130-132
 
 
-def atq_block(W, gram_in=None, gram=None, max_iter=100):
+def atq_block(W, gram_in=None, gram=None, max_iter=100, margin_out=None):
     """init (quantizer.py:49-67) -> ITF with the global stop test (:160-175) -> AGA (:207-246).
-    gram_in: matrix handed to AGA as 'X' (S = X'X); gram: S itself."""
+    gram_in: matrix handed to AGA as 'X' (S = X'X); gram: S itself.
+    margin_out (adjudication aid): a one-element list that receives | |Z| - 0.5 | of the rounding that
+    produced the returned T, i.e. how far every code sits from a threshold tie."""
     mu = W.mean(1, keepdim=True)
     Wc = W - mu
     delta = 0.75 * Wc.abs().mean(1, keepdim=True)
@@ -37,6 +39,8 @@ def atq_block(W, gram_in=None, gram=None, max_iter=100):
         T_prev = T
         alpha, mu = _grid(W, T)
         T = _round(W, alpha, mu)
+    if margin_out is not None:
+        margin_out.append((((W - mu) / alpha.clamp(min=_TINY)).abs() - 0.5).abs())
     S = gram if gram is not None else (gram_in.T @ gram_in if gram_in is not None else None)
     if S is not None:
         s1 = S.sum(1, keepdim=True)                                 # S @ 1
@@ -54,7 +58,7 @@ def ssr_select(W, remaining, block):
     wm = Wr.mean(1, keepdim=True)
     sim = ((Wr / Wr.norm(dim=0, keepdim=True).clamp(min=_TINY)).T @ (wm / wm.norm().clamp(min=_TINY))).squeeze(1)
     top = torch.topk(sim, block).indices                            # reorder.py:133
-    keep = torch.ones(remaining.numel(), dtype=torch.bool)
+    keep = torch.ones(remaining.numel(), dtype=torch.bool, device=remaining.device)
     keep[top] = False
     return remaining[top], remaining[keep]
 
@@ -68,33 +72,49 @@ def hessian_add(H, X):
 def damped_inverse(Hraw, nsamples, percdamp=0.01):
     H = Hraw / nsamples                                             # gptq.py:94-103
     H.diagonal().add_(percdamp * torch.diag(H).mean())
-    return H, torch.cholesky_inverse(torch.linalg.cholesky(H))
+    try:
+        return H, torch.cholesky_inverse(torch.linalg.cholesky(H))
+    except RuntimeError:                                            # gptq.py:104-106
+        return H, torch.linalg.pinv(H)
 
 
-def quantize_layer(W, Hraw, nsamples, block=128, percdamp=0.01, use_ssr=True, aga="hessian", max_iter=100):
-    """gptq.py:78-199."""
+def quantize_layer(W, Hraw, nsamples, block=128, percdamp=0.01, use_ssr=True, aga="hessian", max_iter=100,
+                   static_perm=None, return_margin=False):
+    """gptq.py:78-199 on W's device and dtype (CPU fp32 = the reference's CPU path; a CUDA tensor runs the same ATen
+    calls on the GPU, the reference's own default device, main.py:368).  static_perm: a fixed sweep order (the
+    act-order extension: the reference with use_ssr=False on pre-permuted columns).  return_margin adds a
+    fifth output: | |Z| - 0.5 | per code, in original column positions."""
     W = W.clone()
     n, m = W.shape
+    dev = W.device
     H, Hinv = damped_inverse(Hraw, nsamples, percdamp)
     dinv = torch.diag(Hinv).clamp(min=_TINY)
     T_full = torch.zeros_like(W)
+    margin = torch.zeros_like(W) if return_margin else None
     alphas, mus, perm = [], [], []
-    remaining = torch.arange(m)
+    remaining = torch.arange(m, device=dev)
     done = 0
     while done < m:
         if use_ssr:
             blk, remaining = ssr_select(W, remaining, block)
             rem = remaining
+        elif static_perm is not None:
+            hi = min(done + block, m)
+            blk, rem = static_perm[done:hi], static_perm[hi:]
         else:
-            blk, rem = torch.arange(done, min(done + block, m)), torch.arange(min(done + block, m), m)
+            hi = min(done + block, m)
+            blk, rem = torch.arange(done, hi, device=dev), torch.arange(hi, m, device=dev)
         perm.append(blk)
         Wb = W[:, blk]
+        mo = [] if return_margin else None
         if aga == "hessian":
-            a, u, Tb = atq_block(Wb, gram_in=H[blk][:, blk], max_iter=max_iter)
+            a, u, Tb = atq_block(Wb, gram_in=H[blk][:, blk], max_iter=max_iter, margin_out=mo)
         elif aga == "activations":
-            a, u, Tb = atq_block(Wb, gram=Hraw[blk][:, blk], max_iter=max_iter)
+            a, u, Tb = atq_block(Wb, gram=Hraw[blk][:, blk], max_iter=max_iter, margin_out=mo)
         else:
-            a, u, Tb = atq_block(Wb, max_iter=max_iter)
+            a, u, Tb = atq_block(Wb, max_iter=max_iter, margin_out=mo)
+        if return_margin:
+            margin[:, blk] = mo[0]
         alphas.append(a)
         mus.append(u)
         T_full[:, blk] = Tb
@@ -102,4 +122,5 @@ def quantize_layer(W, Hraw, nsamples, block=128, percdamp=0.01, use_ssr=True, ag
             E = Wb - (a * Tb + u)
             W[:, rem] -= E @ (Hinv[blk][:, rem] / dinv[blk][:, None])   # gptq.py:173-186
         done += blk.numel()
-    return torch.cat(alphas, 1), torch.cat(mus, 1), T_full, torch.cat(perm)
+    out = (torch.cat(alphas, 1), torch.cat(mus, 1), T_full, torch.cat(perm))
+    return out + (margin,) if return_margin else out

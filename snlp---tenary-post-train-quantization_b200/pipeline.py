@@ -41,9 +41,11 @@ class LayerDriver:
         self.block_size, self.percdamp, self.share_inputs = block_size, percdamp, share_inputs
         self.streams = [torch.cuda.Stream(self.device) for _ in range(max(1, num_streams))]
 
-    def quantize(self, linears, use_ssr: bool = True, aga: str = "hessian", max_iter: int = 100, hess_timing=None):
+    def quantize(self, linears, use_ssr: bool = True, aga: str = "hessian", max_iter: int = 100, hess_timing=None,
+                 order: Optional[str] = None):
         """linears: [(name, W (n, m) CUDA fp32, X (.., m) CUDA activations)].  Linears handed the SAME X object
-        share one Hessian when share_inputs is set.  Returns [GPTQ] in order, quantized."""
+        share one Hessian when share_inputs is set.  ``order`` as in GPTQ.quantize ('ssr' | 'sequential' | 'actorder';
+        None follows use_ssr).  Returns [GPTQ] in order, quantized."""
         main = torch.cuda.current_stream(self.device)
         shared = {}
         gs = []
@@ -61,25 +63,26 @@ class LayerDriver:
                 if self.share_inputs:
                     shared[id(X)] = g.state
             gs.append(g)
-        return self.run_chains(gs, use_ssr=use_ssr, aga=aga, max_iter=max_iter)
+        return self.run_chains(gs, use_ssr=use_ssr, aga=aga, max_iter=max_iter, order=order)
 
-    def run_chains(self, gs, use_ssr: bool = True, aga: str = "hessian", max_iter: int = 100):
+    def run_chains(self, gs, use_ssr: bool = True, aga: str = "hessian", max_iter: int = 100, order: Optional[str] = None):
         """Prologue + sweep of every GPTQ in ``gs`` (Hessians already accumulated on the current stream), longest
         chain first, spread over the side streams; returns ``gs`` finished."""
-        return self.finish_chains(gs, self.enqueue_chains(gs, use_ssr=use_ssr, aga=aga, max_iter=max_iter))
+        return self.finish_chains(gs, self.enqueue_chains(gs, use_ssr=use_ssr, aga=aga, max_iter=max_iter, order=order))
 
-    def enqueue_chains(self, gs, use_ssr: bool = True, aga: str = "hessian", max_iter: int = 100):
+    def enqueue_chains(self, gs, use_ssr: bool = True, aga: str = "hessian", max_iter: int = 100,
+                       order: Optional[str] = None):
         """Asynchronous half of run_chains(): returns the order to hand to finish_chains()."""
         main = torch.cuda.current_stream(self.device)
         ready = torch.cuda.Event()
         ready.record(main)
-        order = sorted(range(len(gs)), key=lambda i: -chain_cost(gs[i].rows, gs[i].columns))
-        for slot, i in enumerate(order):
+        seq = sorted(range(len(gs)), key=lambda i: -chain_cost(gs[i].rows, gs[i].columns))
+        for slot, i in enumerate(seq):
             s = self.streams[slot % len(self.streams)]
             s.wait_event(ready)
             with torch.cuda.stream(s):
-                gs[i].enqueue(use_ssr=use_ssr, aga=aga, max_iter=max_iter)
-        return order
+                gs[i].enqueue(use_ssr=use_ssr, aga=aga, max_iter=max_iter, order=order)
+        return seq
 
     def finish_chains(self, gs, order):
         main = torch.cuda.current_stream(self.device)
@@ -101,9 +104,11 @@ def chain_cost(n: int, m: int, block: int = 128) -> float:
 
 class HostPipeline:
     def __init__(self, device, block_size: int = 128, percdamp: float = 0.01, use_ssr: bool = True,
-                 aga: str = "hessian", share_inputs: bool = False, num_streams: int = 3, depth: int = 3):
+                 aga: str = "hessian", share_inputs: bool = False, num_streams: int = 3, depth: int = 3,
+                 order: Optional[str] = None):
         self.device = torch.device(device)
         self.block_size, self.percdamp, self.use_ssr, self.aga = block_size, percdamp, use_ssr, aga
+        self.order = order                            # as in GPTQ.quantize; None follows use_ssr
         self.share_inputs = share_inputs
         self.copy_stream = torch.cuda.Stream(self.device)
         self.out_stream = torch.cuda.Stream(self.device)
@@ -193,7 +198,7 @@ class HostPipeline:
                 s = self.chain_streams[li % len(self.chain_streams)]
                 s.wait_event(x_done)
                 with torch.cuda.stream(s):
-                    g.enqueue(use_ssr=self.use_ssr, aga=self.aga)
+                    g.enqueue(use_ssr=self.use_ssr, aga=self.aga, order=self.order)
             # prefetch now, while this group's kernels run
             top_up()
             out_group = []

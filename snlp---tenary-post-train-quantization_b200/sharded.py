@@ -163,8 +163,9 @@ class ShardedLayer:
             owner = [(-1 - o) if chain_cost(*s) > self.split_threshold * fair else o for o, s in zip(owner, shapes)]
         return owner
 
-    def _quantize_by_linear(self, linears, use_ssr, aga, max_iter, hess_timing):
+    def _quantize_by_linear(self, linears, use_ssr, aga, max_iter, hess_timing, order=None):
         ctx = self.ctx
+        use_ssr = (order == "ssr") if order is not None else use_ssr
         main = torch.cuda.current_stream(ctx.device)
         owner = self.owners([_shape_of(W) for _, W, _ in linears])
         split = [i for i, o in enumerate(owner) if o < 0]
@@ -220,7 +221,7 @@ class ShardedLayer:
             if not torch.is_tensor(W):
                 raise ValueError(f"{linears[i][0]}: this rank owns the linear and needs its weight, not just the shape")
             gs.append(GPTQ(LinearView(W), self.block_size, self.percdamp, hessian=states[i]))
-        order = self._driver.enqueue_chains(gs, use_ssr=use_ssr, aga=aga, max_iter=max_iter)
+        chain_seq = self._driver.enqueue_chains(gs, use_ssr=use_ssr, aga=aga, max_iter=max_iter, order=order)
         # split linears: inverse broadcast, then every rank sweeps its row slab (statistics all-reduced per block)
         slabs = {}
         for i in split:
@@ -241,9 +242,9 @@ class ShardedLayer:
             lo, hi = ctx.row_range(W.shape[0])
             g = GPTQ(LinearView(W[lo:hi]), self.block_size, self.percdamp, hessian=st)
             g.sweep_flags = _lib.SWEEP_ROW_SHARD
-            g.quantize(use_ssr=use_ssr, aga=aga, max_iter=max_iter)
+            g.quantize(use_ssr=use_ssr, aga=aga, max_iter=max_iter, order=order)
             slabs[i] = (g, (lo, hi))
-        self._driver.finish_chains(gs, order)
+        self._driver.finish_chains(gs, chain_seq)
         out = []
         done_whole = dict(zip(mine, gs))
         for i, (name, W, _) in enumerate(linears):
@@ -257,8 +258,9 @@ class ShardedLayer:
                 out.append((name, None, None, None, None, (0, 0)))
         return out
 
-    def quantize(self, linears, use_ssr: bool = True, aga: str = "hessian", max_iter: int = 100, hess_timing=None):
-        """linears: [(name, W (n, m), X_local (this rank's samples, (.., m)))].
+    def quantize(self, linears, use_ssr: bool = True, aga: str = "hessian", max_iter: int = 100, hess_timing=None,
+                 order: Optional[str] = None):
+        """linears: [(name, W (n, m), X_local (this rank's samples, (.., m)))].  ``order`` as in GPTQ.quantize.
         mode 'linears': W is read only on the linear's owner (see owners()); other ranks may pass its (n, m) shape instead;
           returns [(name, alpha, mu, T_int8, perm, (0, n))] with None tensors and rows (0, 0) for linears owned elsewhere;
           a *split* linear (owners() < 0) needs W on every rank (only this rank's row slab is read) and returns row slabs.
@@ -266,8 +268,9 @@ class ShardedLayer:
           [(name, alpha_slab, mu_slab, T_int8_slab, perm, (row_lo, row_hi))] in the input order.
         hess_timing: optional list that receives (start_event, end_event, tokens, m) per Hessian launch."""
         if self.mode == "linears":
-            return self._quantize_by_linear(linears, use_ssr, aga, max_iter, hess_timing)
+            return self._quantize_by_linear(linears, use_ssr, aga, max_iter, hess_timing, order)
         ctx = self.ctx
+        sweep_order = order
         main = torch.cuda.current_stream(ctx.device)
         states = []
         for _, W, X in linears:
@@ -327,7 +330,7 @@ class ShardedLayer:
             g = GPTQ(LinearView(W[lo:hi]), self.block_size, self.percdamp, hessian=st)
             if ctx.world > 1:
                 g.sweep_flags = _lib.SWEEP_ROW_SHARD
-            alpha, mu, _, perm = g.quantize(use_ssr=use_ssr, aga=aga, max_iter=max_iter)
+            alpha, mu, _, perm = g.quantize(use_ssr=use_ssr, aga=aga, max_iter=max_iter, order=sweep_order)
             out[i] = (name, alpha, mu, g.T_int8, perm, (lo, hi))
         return out
 
@@ -340,10 +343,10 @@ class ShardedHostPipeline:
     side stream.  The copies of layer l+1 are enqueued before the kernels of layer l, so they overlap."""
 
     def __init__(self, ctx: ShardContext, block_size: int = 128, percdamp: float = 0.01, use_ssr: bool = True,
-                 aga: str = "hessian", depth: int = 2, mode: str = "linears"):
+                 aga: str = "hessian", depth: int = 2, mode: str = "linears", order: Optional[str] = None):
         self.ctx = ctx
         self.layer = ShardedLayer(ctx, block_size, percdamp, mode=mode)
-        self.use_ssr, self.aga = use_ssr, aga
+        self.use_ssr, self.aga, self.order = use_ssr, aga, order
         self.depth = max(1, int(depth))
         self.copy_stream = torch.cuda.Stream(ctx.device)
         self.out_stream = torch.cuda.Stream(ctx.device)
@@ -427,7 +430,7 @@ class ShardedHostPipeline:
             # With depth slots, depth - 1 layers are ahead; the slot a new layer lands in was freed on the host.
             top_up(self.depth - 1)
             out = self.layer.quantize([(name, wd, x_dev[key]) for (name, _, _, key), wd in zip(lins, w_dev)],
-                                      use_ssr=self.use_ssr, aga=self.aga)
+                                      use_ssr=self.use_ssr, aga=self.aga, order=self.order)
             done = torch.cuda.Event()
             done.record(compute)
             res = []

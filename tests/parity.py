@@ -99,3 +99,64 @@ def assert_model_level_parity(name, got, ref):
         em = scale_rel_err(got["mu"], ref["mu"], mask, floor=np.abs(np.asarray(ref["alpha"], dtype=np.float64)))
         assert em <= 5e-4, f"{name}: mu err (relative to alpha) {em:.3e}"
     return agree
+
+
+def clean_prefix_mask(Ta, Tb, perm, block_size):
+    """Boolean (n, nb): True where the row's codes agree in this block AND in every earlier block of the sweep.  One
+    flipped code changes that row's error feedback, so every LATER block of the row legitimately sees different
+    weights: scales are judged where no earlier flip has touched the row."""
+    pairs = block_pairs_agree(Ta, Tb, perm, block_size)
+    return np.logical_and.accumulate(pairs, axis=1)
+
+
+def adjudicate(got, ref, margin=None, block_size=128):
+    """SURVEY 8c adjudication of one layer: got / ref are dicts with alpha, mu, T, perm; ``margin`` (optional, (n, m)) is
+    | |Z| - 0.5 | of the reference's final rounding per code (original positions).  Returns a JSON-able report:
+    code agreement, block membership, scale errors on clean (row, block) pairs, and for every row that diverges the
+    smallest margin among its disagreeing codes in the FIRST block where it diverges (tie evidence)."""
+    Tg, Tr = np.asarray(got["T"]).astype(np.int8), np.asarray(ref["T"]).astype(np.int8)
+    pg, pr = np.asarray(got["perm"]), np.asarray(ref["perm"])
+    n, m = Tr.shape
+    nb = (m + block_size - 1) // block_size
+    same_sets = [bool(np.array_equal(np.sort(pg[k:k + block_size]), np.sort(pr[k:k + block_size])))
+                 for k in range(0, m, block_size)]
+    rep = {"n": int(n), "m": int(m), "code_agreement": code_agreement(Tg, Tr), "perm_equal": bool(np.array_equal(pg, pr)),
+           "blocks": nb, "blocks_same_membership": int(sum(same_sets)),
+           "first_block_same_membership": bool(same_sets[0])}
+    lead = 0                                     # leading blocks with identical membership: comparable block by block
+    for ok in same_sets:
+        if not ok:
+            break
+        lead += 1
+    rep["leading_blocks_same_membership"] = lead
+    if lead == 0:
+        return rep
+    cols_ok = lead * block_size
+    pairs = block_pairs_agree(Tg, Tr, pr, block_size)[:, :lead]
+    clean = np.logical_and.accumulate(pairs, axis=1)
+    a_ref = np.asarray(ref["alpha"], dtype=np.float64)[:, :lead]
+    sane = np.isfinite(a_ref) & (np.abs(a_ref) < 1e3)           # rows the reference's AGA blew up (SURVEY Q9)
+    mask = clean & sane
+    rep["pairs"] = int(pairs.size)
+    rep["pairs_disagreeing"] = int((~pairs).sum())
+    rep["rows_diverged"] = int((~clean[:, -1]).sum())
+    rep["q9_pairs_excluded"] = int((~sane).sum())
+    # the block order inside a membership-equal prefix may differ only by in-block swaps: alpha/mu of block k are the same
+    # quantity on both sides
+    rep["alpha_rel_err_max"] = scale_rel_err(np.asarray(got["alpha"])[:, :lead], a_ref, mask)
+    rep["mu_err_rel_alpha_max"] = scale_rel_err(np.asarray(got["mu"])[:, :lead], np.asarray(ref["mu"])[:, :lead], mask,
+                                                floor=np.abs(a_ref))
+    if margin is not None and rep["rows_diverged"]:
+        margin = np.asarray(margin, dtype=np.float64)
+        first_bad = np.argmin(clean, axis=1)                    # first block where the row is no longer clean
+        mins = []
+        for r in np.nonzero(~clean[:, -1])[0]:
+            cols = pr[first_bad[r] * block_size:(first_bad[r] + 1) * block_size]
+            bad = cols[Tg[r, cols] != Tr[r, cols]]
+            if bad.size:
+                mins.append(float(margin[r, bad].min()))
+        if mins:
+            mins = np.sort(np.asarray(mins))
+            rep["tie_margin_first_divergence"] = {"rows": int(mins.size), "median": float(np.median(mins)),
+                                                  "p90": float(mins[int(0.9 * (mins.size - 1))]), "max": float(mins[-1])}
+    return rep

@@ -1,0 +1,143 @@
+"""Parity AT THE BENCH'S OWN SHAPES (BASELINE.json configs[1]/[2]: the LLaMA-2-7B linears) against the oracle --
+``oracle/torch_port.py``, the restatement of /root/reference/gptq.py:78-199 that is pinned to the unmodified reference's
+outputs (tests/test_oracle_golden.py) -- on identical inputs: fp16 synthetic activations, 16 384 tokens, lambda = 0.5,
+W ~ N(0, 0.02^2).  The CUDA path computes its own Hessian with the tcgen05 kernel from the fp16 activations;
+the oracle computes X'X in fp32 on the host from the same values, so the two sides differ exactly where the reference
+and the product differ: accumulation order and the fp32-emulating tensor-core GEMMs.
+
+Tolerances are north_star's: codes >= 99.9 %, alpha / mu within 1e-4 relative on (row, block) pairs no earlier flip has
+touched, reconstruction error within 1e-3 relative.  Every disagreement is adjudicated: the margin
+| |Z| - 0.5 | of the reference's rounding at the first block where a row diverges -- a threshold tie -- is reported and
+bounded.  With SSR one swapped top-k boundary legitimately de-correlates everything after it (the reference does not
+reproduce itself there), so SSR cases assert block by block on the leading blocks whose membership
+agrees, always the first block, and the reconstruction error; the report says how many blocks agreed.
+
+Reports land in gpurun_out/parity_benchshape.json (copied to profiles/ by hand)."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import parity
+from oracle import torch_port
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+NT = 16384
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_inputs = {}
+_report = {}
+
+
+def _activations(m):
+    """fp16 (NT, m) on the device + the oracle's fp32 Hessian of the same values (host sgemm), cached per width."""
+    if m not in _inputs:
+        g = torch.Generator(device=DEV).manual_seed(4000 + m)
+        r, lam = 64, 0.5
+        B = torch.randn((r, m), device=DEV, generator=g)
+        X = (torch.randn((NT, m), device=DEV, generator=g)
+             + (lam / r ** 0.5) * (torch.randn((NT, r), device=DEV, generator=g) @ B)).to(torch.float16)
+        Xc = X.float().cpu()
+        torch.set_num_threads(os.cpu_count() or 8)
+        H = Xc.T @ Xc                                                    # gptq.py:74-75 on the host cores
+        _inputs.clear()                                                  # one width resident at a time
+        _inputs[m] = (X, H)
+    return _inputs[m]
+
+
+def _weight(n, m):
+    g = torch.Generator(device=DEV).manual_seed(17 * n + m)
+    return torch.randn((n, m), device=DEV, generator=g) * 0.02
+
+
+def _recon(W, Wq, H):
+    D = (W - Wq).double()
+    Hd = H.double()
+    return float(torch.sqrt((D @ Hd * D).sum() / ((W.double() @ Hd) * W.double()).sum()))
+
+
+def _dequant(alpha, mu, T, perm, block=128):
+    Wq = torch.empty_like(T)
+    for k in range(alpha.shape[1]):
+        cols = perm[k * block:(k + 1) * block]
+        Wq[:, cols] = alpha[:, k:k + 1] * T[:, cols] + mu[:, k:k + 1]
+    return Wq
+
+
+def _save(tag, rep):
+    _report[tag] = rep
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_benchshape.json"), "w") as f:
+            json.dump(_report, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+    print(tag, json.dumps(rep))
+
+
+@pytest.mark.parametrize("n,m,order", [(4096, 4096, "sequential"), (4096, 4096, "ssr"), (11008, 4096, "sequential"),
+                                       (4096, 11008, "sequential"), (4096, 11008, "ssr")])
+def test_bench_shape_layer_vs_oracle(n, m, order):
+    import tq100
+    from tq100.pipeline import LinearView
+    X, H_ref = _activations(m)
+    W = _weight(n, m)
+    use_ssr = order == "ssr"
+    q = tq100.GPTQ(LinearView(W))
+    q.add_batch(X.reshape(NT // 2048, 2048, m))
+    alpha, mu, T, perm = q.quantize(use_ssr=use_ssr)
+    assert q.info == 0
+    Wq = q.get_quantized_weight()
+    Wc = W.cpu()
+    ra, ru, rT, rp, margin = torch_port.quantize_layer(Wc, H_ref, NT, 128, 0.01, use_ssr=use_ssr, return_margin=True)
+    got = dict(alpha=alpha.cpu().numpy(), mu=mu.cpu().numpy(), T=T.cpu().numpy(), perm=perm.cpu().numpy())
+    ref = dict(alpha=ra.numpy(), mu=ru.numpy(), T=rT.numpy(), perm=rp.numpy())
+    rep = parity.adjudicate(got, ref, margin.numpy())
+    e_got = _recon(Wc, Wq.cpu(), H_ref)
+    e_ref = _recon(Wc, _dequant(ra, ru, rT, rp), H_ref)
+    rep.update(recon_got=e_got, recon_ref=e_ref, recon_rel_diff=abs(e_got - e_ref) / e_ref, order=order, tokens=NT)
+    _save(f"{n}x{m}_{order}", rep)
+
+    assert rep["recon_rel_diff"] <= parity.RECON_RTOL, rep
+    assert rep["first_block_same_membership"], rep
+    lead = rep["leading_blocks_same_membership"]
+    if not use_ssr:
+        assert rep["perm_equal"] and lead == rep["blocks"], rep
+    if lead == rep["blocks"]:
+        assert rep["code_agreement"] >= parity.CODE_AGREEMENT, rep
+    else:
+        # SSR after a swapped top-k boundary: codes of the membership-equal prefix are still held to the bar
+        cols = ref["perm"][:lead * 128]
+        agree = float((got["T"][:, cols] == ref["T"][:, cols]).mean())
+        rep["code_agreement_leading_blocks"] = agree
+        _save(f"{n}x{m}_{order}", rep)
+        assert agree >= parity.CODE_AGREEMENT, rep
+    assert rep["alpha_rel_err_max"] <= parity.SCALE_RTOL, rep
+    assert rep["mu_err_rel_alpha_max"] <= parity.SCALE_RTOL, rep
+    tie = rep.get("tie_margin_first_divergence")
+    if tie is not None:
+        # disagreements start at threshold ties: a code flips only where |Z| sits within fp32 noise of 0.5
+        assert tie["median"] <= 1e-3, rep
+
+
+def test_oracle_fp32_vs_fp64_floor_4096():
+    """The noise floor every number above is read against: the oracle in fp32 vs the same oracle in fp64
+    on the same 4096 x 4096 sequential case.  Recorded, and the CUDA path must sit within 10x of the floor's disagreeing
+    (row, block) pairs (at least 50, so an exact-agreement floor does not make the bound vacuous)."""
+    n = m = 4096
+    X, H_ref = _activations(m)
+    Wc = _weight(n, m).cpu()
+    a32, u32, T32, p32 = torch_port.quantize_layer(Wc, H_ref, NT, 128, 0.01, use_ssr=False)
+    Xd = X.double().cpu()
+    H64 = Xd.T @ Xd
+    a64, u64, T64, p64, margin = torch_port.quantize_layer(Wc.double(), H64, NT, 128, 0.01, use_ssr=False, return_margin=True)
+    r64 = dict(alpha=a64.numpy(), mu=u64.numpy(), T=T64.numpy(), perm=p64.numpy())
+    floor = parity.adjudicate(dict(alpha=a32.numpy(), mu=u32.numpy(), T=T32.numpy(), perm=p32.numpy()), r64, margin.numpy())
+    _save("floor_4096x4096_sequential_ref32_vs_ref64", floor)
+    got = _report.get("4096x4096_sequential")
+    if got is not None:
+        assert got["pairs_disagreeing"] <= max(50, 10 * floor["pairs_disagreeing"]), (got, floor)

@@ -61,7 +61,9 @@ def test_full_size_layer_properties(n, m, order):
     Hd, Hinv, _ = q.state.damped_inverse(q.percdamp)
     v = torch.randn((m, 8), dtype=torch.float64, device=DEV)
     resid = (Hd.double() @ (Hinv.double() @ v) - v).abs().max().item()
-    assert resid < 2e-3, resid
+    # DESIGN section 3 measures 2-3e-5 at these sizes; an order of magnitude of slack, tight enough that a regression of the
+    # split-TF32 updates (plain TF32 gives ~1e-3) cannot hide
+    assert resid < 2e-4, resid
     assert torch.equal(torch.sort(perm).values, torch.arange(m, device=DEV))
     assert set(torch.unique(q.T_int8).tolist()) <= {-1, 0, 1}
     nb = (m + 127) // 128

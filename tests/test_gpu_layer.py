@@ -248,3 +248,29 @@ def test_host_pipeline_matches_device_api(share, depth):
     x_bytes = sum(x.numel() * 2 for x, _ in groups)
     w_bytes = sum(w.numel() * 4 for _, e in groups for _, w in e)
     assert pipe.h2d_bytes == 4 * (x_bytes + w_bytes)
+
+
+@pytest.mark.parametrize("tag", ["seq", "ssr"])
+def test_non_pd_hessian_takes_the_pinv_route(tag, golden_dir):
+    """gptq.py:101-106: Cholesky fails on an indefinite H, the reference continues on torch.linalg.pinv.  Here
+    tq_chol_inverse reports the failing pivot through `info`, GPTQ.finish() re-runs the whole sweep on the library
+    pseudo-inverse.  Compared with the unmodified reference's outputs (tests/golden/gptq_pinv.npz)."""
+    import tq100
+    g = np.load(os.path.join(golden_dir, "gptq_pinv.npz"))
+    W, H = g["W"], g["H"]
+    q = tq100.GPTQ(_layer(W), block_size=128, percdamp=0.01)
+    q.H = torch.from_numpy(H.copy())                          # the reference's attributes (gptq.py:50-51)
+    q.nsamples = 1
+    alpha, mu, T, perm = q.quantize(use_ssr=(tag == "ssr"))
+    assert q.info > 0                                         # 1-based index of the first non-positive pivot
+    Hd, Hinv, info = q.state.damped_inverse(q.percdamp)       # the cache now holds the pseudo-inverse
+    assert int(info.item()) == 0
+    eye = (Hd.double() @ Hinv.double()).cpu().numpy()
+    assert np.abs(eye - np.eye(H.shape[0])).max() < 1e-3      # pinv of a nonsingular matrix is its inverse
+    got = dict(alpha=alpha.cpu().numpy(), mu=mu.cpu().numpy(), T=T.cpu().numpy(), perm=perm.cpu().numpy())
+    ref = dict(alpha=g[f"{tag}_alpha"], mu=g[f"{tag}_mu"], T=g[f"{tag}_T"], perm=g[f"{tag}_perm"])
+    parity.assert_layer_parity(got, ref, what=f"pinv route/{tag}")
+    # a second linear sharing the state reuses the cached pseudo-inverse without failing again
+    q2 = tq100.GPTQ(_layer(W), block_size=128, percdamp=0.01, hessian=q.state)
+    a2, u2, T2, p2 = q2.quantize(use_ssr=(tag == "ssr"))
+    assert q2.info == 0 and torch.equal(T2, T) and torch.equal(p2, perm)

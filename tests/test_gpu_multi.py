@@ -22,9 +22,6 @@ def test_sharded_layer_matches_single_gpu():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")
-@pytest.mark.skipif(os.environ.get("TQ_TEST_SHARDED_MODEL") != "1",
-                    reason="sharded whole-model driver: verified with gloo on CPU (tests/test_model_driver_sharded_cpu.py); "
-                           "its NCCL run has not been on a GPU box yet -- set TQ_TEST_SHARDED_MODEL=1 to run it")
 def test_sharded_whole_model_matches_reference():
     n = min(torch.cuda.device_count(), 4)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
