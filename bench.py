@@ -27,7 +27,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-LLAMA2_7B = dict(name="llama-2-7b", d=4096, ffn=11008, layers=32)
+LLAMA2_7B = dict(name="LLaMA-2-7B", d=4096, ffn=11008, layers=32)
+LLAMA2_13B = dict(name="LLaMA-2-13B", d=5120, ffn=13824, layers=40)
 SAMPLES, SEQ = 128, 2048
 # (linear name, out_features n, in_features m, which of the layer's inputs it reads)
 def linears(cfg):
@@ -96,80 +97,226 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------ CPU arm
-def cpu_arm(threads=None, hess_tokens=16384):
-    """The reference's CPU implementation of the path on the host cores.  The reference is pure
-    Python/PyTorch and cannot travel to the GPU box, so this is the oracle's torch-CPU port
-    (oracle/torch_port.py: same library, oneMKL + LAPACK, all threads), on a bounded sample: ONE
-    4096x4096 linear -- Hessian over `hess_tokens` of the 262144 tokens (cost is exactly linear in
-    tokens, gptq.py:75) + the damped inverse + the full SSR sweep -- extrapolated to the model by
-    stage: Hessian by 2*Nt*m^2, inverse by m^3, sweep by n*m^2."""
-    import torch
-    from oracle import torch_port
-    cores = threads or os.cpu_count()
-    torch.set_num_threads(cores)
-    n = m = 4096
-    g = torch.Generator().manual_seed(1)
+# ------------------------------------------------------------------------------------ reference arm
+def find_reference_dir():
+    """The unmodified reference, if this machine has it: $TQ_REFERENCE_DIR, baseline/_ref, /root/reference.
+    It is a flat directory of Python scripts, not an installable package, and does not exist on the GPU box; there the
+    oracle's port (oracle/torch_port.py, pinned to the reference's outputs by tests/test_oracle_golden.py) stands in."""
+    for d in (os.environ.get("TQ_REFERENCE_DIR"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if d and os.path.isfile(os.path.join(d, "gptq.py")) and os.path.isfile(os.path.join(d, "quantizer.py")):
+            return d
+    return None
+
+
+def load_reference_gptq(ref_dir):
+    """Import the reference's gptq module under an isolated loader: its modules are flat top-level names (gptq.py:17-18
+    does `from quantizer import ...`) that collide with this repo's mirror; nothing is written into the reference dir."""
+    import importlib.util
+    sys.dont_write_bytecode = True
+    names = ("quantizer", "reorder", "gptq")
+    saved = {k: sys.modules.get(k) for k in names}
+    mods = {}
+    try:
+        for name in names:
+            spec = importlib.util.spec_from_file_location(name, os.path.join(ref_dir, name + ".py"))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[name] = mod
+            spec.loader.exec_module(mod)
+            mods[name] = mod
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mods["gptq"]
+
+
+class ReferenceRunner:
+    """The reference's implementation of the path for ONE linear: GPTQ.add_batch per calibration sample (gptq.py:59-76)
+    and GPTQ.quantize (gptq.py:78-199), fp32, on `device` ('cpu': all host threads; 'cuda': the reference's own default
+    device, main.py:368, TF32 off).  kind 'reference' = the unmodified reference's class; 'port' = oracle/torch_port.py,
+    the same ATen call sequence."""
+
+    def __init__(self, device="cpu", threads=None, order="ssr"):
+        import torch
+        self.torch = torch
+        self.device = torch.device(device)
+        self.order = order
+        self.cores = threads or os.cpu_count()
+        if self.device.type == "cpu":
+            torch.set_num_threads(self.cores)
+        else:
+            torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.allow_tf32 = False
+        self.ref_dir = find_reference_dir()
+        self.kind = "reference" if self.ref_dir else "port"
+        if self.ref_dir:
+            self.G = load_reference_gptq(self.ref_dir)
+        else:
+            from oracle import torch_port
+            self.port = torch_port
+
+    def _sync(self):
+        if self.device.type == "cuda":
+            self.torch.cuda.synchronize(self.device)
+
+    def run(self, W, samples):
+        """W (n, m) fp32 on the device; samples: iterable of (L, m) activations (any float dtype, on the device).
+        Returns (hessian_seconds, quantize_seconds, outputs dict)."""
+        torch = self.torch
+        n, m = W.shape
+        use_ssr = self.order == "ssr"
+        static_perm = None
+        if self.kind == "reference" and self.order != "actorder":
+            layer = torch.nn.Linear(m, n, bias=False, device=self.device)
+            layer.weight.data = W
+            g = self.G.GPTQ(layer, block_size=128, percdamp=0.01)
+            self._sync()
+            t0 = time.perf_counter()
+            for x in samples:
+                g.add_batch(x.float())
+            self._sync()
+            t_h = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            alpha, mu, T, perm = g.quantize(use_ssr=use_ssr)
+            self._sync()
+            t_q = time.perf_counter() - t0
+        else:
+            from oracle import torch_port
+            H = torch.zeros((m, m), device=self.device)
+            ns = 0
+            self._sync()
+            t0 = time.perf_counter()
+            for x in samples:
+                ns += torch_port.hessian_add(H, x.float())
+            self._sync()
+            t_h = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            if self.order == "actorder":
+                # the act-order extension's oracle (SURVEY 8c): the reference's sequential sweep in descending-diag(H) order
+                static_perm = torch.argsort(torch.diagonal(H), descending=True, stable=True)
+            alpha, mu, T, perm = torch_port.quantize_layer(W, H, ns, 128, 0.01, use_ssr=use_ssr, static_perm=static_perm)
+            self._sync()
+            t_q = time.perf_counter() - t0
+        return t_h, t_q, dict(alpha=alpha, mu=mu, T=T, perm=perm)
+
+
+def synth_linear_cpu(torch, n, m, tokens, seed):
+    """W ~ N(0, 0.02^2); activations Z + 0.5 F B / 8 rounded once to fp16, as (tokens / SEQ) samples."""
+    g = torch.Generator().manual_seed(seed)
     W = torch.randn((n, m), generator=g) * 0.02
     Bm = torch.randn((64, m), generator=g)
-    X = torch.randn((hess_tokens, m), generator=g) + (0.5 / 8.0) * (torch.randn((hess_tokens, 64), generator=g) @ Bm)
+    X = torch.randn((tokens, m), generator=g) + (0.5 / 8.0) * (torch.randn((tokens, 64), generator=g) @ Bm)
     X = X.half().float()
-    t0 = time.perf_counter()
-    H = torch.zeros((m, m))
-    ns = 0
-    for i in range(0, hess_tokens, SEQ):
-        ns += torch_port.hessian_add(H, X[i:i + SEQ])
-    t_h = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    torch_port.damped_inverse(H, ns, 0.01)
-    t_inv = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    torch_port.quantize_layer(W, H, ns, 128, 0.01, use_ssr=True, aga="hessian")
-    t_q = time.perf_counter() - t0            # includes one more damped inverse
-    t_sweep = max(t_q - t_inv, 1e-9)
-    cfg = LLAMA2_7B
-    tot_h = tot_inv = tot_sw = 0.0
-    for _, nn_, mm_, _ in linears(cfg):
-        tot_h += t_h * (SAMPLES * SEQ / hess_tokens) * (mm_ / m) ** 2
-        tot_inv += t_inv * (mm_ / m) ** 3
-        tot_sw += t_sweep * (nn_ / n) * (mm_ / m) ** 2
-    total = cfg["layers"] * (tot_h + tot_inv + tot_sw)
-    return {"value": total, "unit": "s", "cores": cores, "kind": "port",
-            "sample": (f"oracle/torch_port.py (torch CPU fp32, {cores} threads), one 4096x4096 linear: Hessian over "
-                       f"{hess_tokens} of {SAMPLES * SEQ} tokens ({t_h:.2f} s), damped inverse ({t_inv:.2f} s), "
-                       f"full SSR sweep ({t_sweep:.2f} s); extrapolated to 32 layers x 7 linears "
-                       f"(Hessian ~ 2*Nt*m^2, inverse ~ m^3, sweep ~ n*m^2)"),
-            "measured_s": t_h + t_inv + t_q}
+    return W, [X[i:i + SEQ] for i in range(0, tokens, SEQ)]
+
+
+def cpu_layer_sample(cfg, order, steps=1, budget_s=None, hess_tokens=16384, threads=None, log=None):
+    """The reference arm's bounded sample: ONE transformer layer's 7 linears on the host cores.
+    Per linear: add_batch over `hess_tokens` of the 262144 calibration tokens (cost exactly linear in tokens,
+    gptq.py:75) and the FULL quantize().  `steps` passes rotate over the linears -- step s measures linear s mod 7 (with
+    fewer than 7 steps, several per step) -- so every linear is measured at least once; repeat measurements stop when
+    `budget_s` of wall clock is used up.  Model estimate = layers x sum over linears of (mean add_batch x tokens factor +
+    mean quantize)."""
+    import torch
+    runner = ReferenceRunner("cpu", threads=threads, order=order)
+    lins = linears(cfg)
+    k = max(1, steps)
+    plan = [[j for j in range(len(lins)) if j % k == s] for s in range(k)] if k < len(lins) else \
+           [[s % len(lins)] for s in range(k)]
+    t_h = {j: [] for j in range(len(lins))}
+    t_q = {j: [] for j in range(len(lins))}
+    t_start = time.perf_counter()
+    steps_measured = 0
+    for s, js in enumerate(plan):
+        covered = all(t_q[j] for j in range(len(lins)))
+        if covered and budget_s is not None and time.perf_counter() - t_start > budget_s:
+            break
+        for j in js:
+            name, n, m, _ = lins[j]
+            W, samples = synth_linear_cpu(torch, n, m, hess_tokens, seed=1000 + j)
+            th, tq, _ = runner.run(W, samples)
+            t_h[j].append(th)
+            t_q[j].append(tq)
+            if log:
+                log(f"[reference arm] step {s} {name} {n}x{m}: add_batch({hess_tokens} tokens) {th:.2f} s, quantize {tq:.2f} s")
+        steps_measured += 1
+    tok_factor = SAMPLES * SEQ / hess_tokens
+    mean = lambda v: sum(v) / len(v)
+    per_layer_h = sum(mean(t_h[j]) for j in t_h if t_h[j]) * tok_factor
+    per_layer_q = sum(mean(t_q[j]) for j in t_q if t_q[j])
+    measured_layer = sum(mean(t_h[j]) + mean(t_q[j]) for j in t_h if t_h[j])
+    total = cfg["layers"] * (per_layer_h + per_layer_q)
+    detail = {lins[j][0]: {"shape": [lins[j][1], lins[j][2]], "add_batch_s": mean(t_h[j]), "quantize_s": mean(t_q[j]),
+                           "measurements": len(t_q[j])} for j in t_h if t_h[j]}
+    src = runner.ref_dir if runner.kind == "reference" else "oracle/torch_port.py"
+    return {"value": total, "unit": "s", "cores": runner.cores, "kind": runner.kind, "source": src,
+            "sample": (f"{'unmodified reference gptq.GPTQ' if runner.kind == 'reference' else 'oracle/torch_port.py'} "
+                       f"(torch CPU fp32, {runner.cores} threads) on ONE transformer layer's 7 linears: add_batch over "
+                       f"{hess_tokens} of {SAMPLES * SEQ} tokens per linear + the full quantize(order={order}); "
+                       f"measured {measured_layer:.1f} s per layer pass; estimate = {cfg['layers']} layers x "
+                       f"(add_batch x {tok_factor:.0f} + quantize)"),
+            "extrapolated": True,
+            "extrapolation": {"measured_layer_s": measured_layer, "tokens_factor": tok_factor, "layers_factor": cfg["layers"],
+                              "per_layer_add_batch_s": per_layer_h, "per_layer_quantize_s": per_layer_q,
+                              "overall_factor": total / measured_layer if measured_layer > 0 else None,
+                              "steps_measured": steps_measured, "wall_s": time.perf_counter() - t_start},
+            "per_linear": detail}
 
 
 def run_reference(args, rank):
+    """`--impl reference`: rank 0 alone runs; the other ranks exit 0 without work."""
     if rank != 0:
         return
-    for _ in range(args.warmup):
-        pass                                   # BLAS needs no warm-up beyond the first call inside the sample
-    vals = []
-    for _ in range(max(1, args.steps)):
-        vals.append(cpu_arm())
-    best = min(vals, key=lambda r: r["value"])
-    v = sum(r["value"] for r in vals) / len(vals)
-    line = {"impl": "reference", "metric": "LLaMA-2-7B ternary PTQ wall-time", "value": v, "unit": "s",
+    cfg, order = bench_config(args)
+    import torch
+    if args.warmup > 0:                      # thread pool + BLAS warm-up on a small layer (not part of any measurement)
+        W, samples = synth_linear_cpu(torch, 256, 512, 2048, seed=1)
+        ReferenceRunner("cpu", order=order).run(W, samples)
+    budget = float(os.environ.get("TQ_REF_BUDGET_S", 200))
+    r = cpu_layer_sample(cfg, order, steps=args.steps, budget_s=budget,
+                         log=(lambda m: print(m, file=sys.stderr, flush=True)))
+    v = r["value"]
+    line = {"impl": "reference", "metric": METRIC[args.config], "value": v, "unit": "s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": v * 1e3,
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, reference=True),
-            "cpu_baseline": {k: best[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "extrapolated": True,
+            "extrapolation_note": ("value is an ESTIMATE of the whole-model time from one measured transformer layer: "
+                                   f"add_batch measured on 1/{r['extrapolation']['tokens_factor']:.0f} of the tokens (linear in "
+                                   f"tokens) and every layer being identical ({cfg['layers']} layers); measured wall "
+                                   f"{r['extrapolation']['wall_s']:.0f} s; steps x ms_per_step therefore exceeds the run time"),
+            "cpu_baseline": r,
             "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    line["cpu_baseline"]["value"] = v
     print(json.dumps(line), flush=True)
 
 
+def bench_config(args):
+    """(model shape dict, sweep order) of --config."""
+    if args.config == "13b-actorder":
+        return dict(LLAMA2_13B, layers=args.layers or LLAMA2_13B["layers"]), "actorder"
+    return dict(LLAMA2_7B, layers=args.layers or LLAMA2_7B["layers"]), "ssr"
+
+
+METRIC = {"7b-ssr": "LLaMA-2-7B ternary PTQ wall-time", "13b-actorder": "LLaMA-2-13B ternary PTQ wall-time",
+          "layer-sweep": "single-layer sweep: Hessian + column-sweep kernels vs roofline"}
+
+
 def workload_config(args, reference=False):
-    return {"workload": "LLaMA-2-7B-shaped ternary GPTQ with SSR column reordering "
-                        "(32 layers x {q,k,v,o 4096x4096; gate,up 11008x4096; down 4096x11008}, "
+    cfg, order = bench_config(args)
+    d, f, L = cfg["d"], cfg["ffn"], cfg["layers"]
+    act_gb = SAMPLES * SEQ * (3 * d + f) * 2 / 1e9
+    w_gb = L * (4 * d * d + 3 * d * f) * 4 / 1e9
+    what = {"ssr": "SSR column reordering", "actorder": "act-order (descending diag(H)) column order"}[order]
+    return {"workload": f"{cfg['name']}-shaped ternary GPTQ with {what} "
+                        f"({L} layers x {{q,k,v,o {d}x{d}; gate,up {f}x{d}; down {d}x{f}}}, "
                         "128x2048 calibration tokens per linear, block 128, percdamp 0.01, ITF + AGA(hessian))",
-            "baseline_config": "configs[1]", "order": "ssr", "aga": "hessian", "block_size": 128,
-            "activations": "fp16, one layer's 4 distinct inputs (12.2 GB) reused for all 32 layers",
-            "cache": "inputs (12.2 GB activations + 25.9 GB weights) far exceed the 126 MB L2; no explicit flush",
+            "baseline_config": "configs[1]" if args.config == "7b-ssr" else "configs[3]", "order": order, "aga": "hessian",
+            "block_size": 128,
+            "activations": f"fp16, one layer's 4 distinct inputs ({act_gb:.1f} GB) reused for all {L} layers",
+            "cache": f"inputs ({act_gb:.1f} GB activations + {w_gb:.1f} GB weights) far exceed the 126 MB L2; no explicit flush",
             "hessians_per_layer": 7, "streams": args.streams, "parallelism": "1 GPU" if args.gpus == 1 else (
                 f"{args.gpus} GPUs: Hessian sample-sharded, NCCL reduce of each H onto the rank that owns the linear, "
                 "whole linears dealt to ranks (no collective inside their sweeps); a linear whose chain exceeds 1.5x a "
@@ -177,6 +324,131 @@ def workload_config(args, reference=False):
                 if getattr(args, "shard_mode", "linears") == "linears" else
                 f"{args.gpus} GPUs: Hessian sample-sharded + NCCL allreduce, H^-1 dealt + broadcast, sweep row-sharded "
                 "(SSR statistics all-reduced per block)")}
+
+
+# ------------------------------------------------------------------------------------ parity of the timed run
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def parity_summary(got, ref, aids=None):
+    """SURVEY 8c adjudication (tests/parity.py) of one linear, reduced to the fields a bench line can carry."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity
+    rep = parity.adjudicate({k: _np(v) for k, v in got.items()}, {k: _np(v) for k, v in ref.items()}, aids)
+    keep = {k: rep.get(k) for k in ("n", "m", "code_agreement", "perm_equal", "blocks", "leading_blocks_same_membership",
+                                     "first_block_same_membership", "pairs", "pairs_disagreeing", "rows_diverged",
+                                     "alpha_rel_err_max", "mu_err_rel_alpha_max")}
+    lead = rep["leading_blocks_same_membership"]
+    if 0 < lead < rep["blocks"]:
+        import numpy as np
+        cols = _np(ref["perm"])[:lead * 128]
+        keep["code_agreement_leading_blocks"] = float((_np(got["T"])[:, cols] == _np(ref["T"])[:, cols]).mean())
+    return keep
+
+
+def recon_error(torch, W, alpha, mu, T, perm, H, block=128):
+    """||(W - Wq) X|| / ||W X|| through H = X'X, fp64, on the device (gptq.py:201-230 dequantisation on both sides)."""
+    Wq = torch.empty_like(W, dtype=torch.float64)
+    perm = perm.long()
+    for k in range(alpha.shape[1]):
+        cols = perm[k * block:(k + 1) * block]
+        Wq[:, cols] = alpha[:, k:k + 1].double() * T[:, cols].double() + mu[:, k:k + 1].double()
+    D = W.double() - Wq
+    Hd = H.double()
+    return float(torch.sqrt((D @ Hd * D).sum() / ((W.double() @ Hd) * W.double()).sum()))
+
+
+# ------------------------------------------------------------------------------------ same-box reference + parity
+def reference_cuda_leg(torch, args, cfg, order, lins, w0, acts, driver, dev):
+    runner = ReferenceRunner(dev, order=order)
+    outs, detail = {}, {}
+    t_h_all = t_q_all = 0.0
+    for name, n, m, src in lins:
+        x = acts[src]
+        th, tq, out = runner.run(w0[name].clone(), (x[i] for i in range(x.shape[0])))
+        outs[name] = out
+        detail[name] = {"shape": [n, m], "add_batch_s": th, "quantize_s": tq}
+        t_h_all += th
+        t_q_all += tq
+    layer_s = t_h_all + t_q_all
+    hess_flops = sum(2.0 * SAMPLES * SEQ * m * m for _, _, m, _ in lins)
+    ref = {"value": cfg["layers"] * layer_s, "unit": "s", "device": torch.cuda.get_device_name(dev), "kind": runner.kind,
+           "measured_layer_s": layer_s, "layers_factor": cfg["layers"], "extrapolated": True,
+           "add_batch_s_per_layer": t_h_all, "quantize_s_per_layer": t_q_all,
+           "add_batch_tflops_dense_fp32": hess_flops / t_h_all / 1e12,
+           "note": (f"{'unmodified reference gptq.GPTQ' if runner.kind == 'reference' else 'oracle/torch_port.py'} with "
+                    "device='cuda' (main.py:368), fp32, TF32 off: one transformer layer's 7 linears, all "
+                    f"{SAMPLES * SEQ} tokens, order={order}; value = measured layer x {cfg['layers']} layers"),
+           "per_linear": detail}
+    if args.no_parity:
+        return ref, None
+    # the product on the same layer-0 inputs (one untimed pass of the bench's own inner loop)
+    gs = driver.quantize([(name, w0[name], acts[src]) for name, n, m, src in lins], use_ssr=order == "ssr", order=order)
+    torch.cuda.synchronize()
+    par = {"against": ref["note"].split(":")[0], "tolerances": "north_star: codes >= 0.999, scales 1e-4, recon 1e-3 (relative)",
+           "linears": {}}
+    worst_code, worst_recon = 1.0, 0.0
+    for (name, n, m, src), g in zip(lins, gs):
+        o = outs[name]
+        got = dict(alpha=g.alpha, mu=g.mu, T=g.T_int8, perm=g.perm)
+        rep = parity_summary(got, o)
+        H = g.H
+        e_got = recon_error(torch, w0[name], g.alpha, g.mu, g.T_int8, g.perm, H)
+        e_ref = recon_error(torch, w0[name], o["alpha"], o["mu"], o["T"], o["perm"], H)
+        rep["recon_got"], rep["recon_ref"] = e_got, e_ref
+        rep["recon_rel_diff"] = abs(e_got - e_ref) / e_ref
+        par["linears"][name] = rep
+        code = rep.get("code_agreement_leading_blocks", rep["code_agreement"])
+        worst_code, worst_recon = min(worst_code, code), max(worst_recon, rep["recon_rel_diff"])
+    par["min_code_agreement_on_comparable_blocks"] = worst_code
+    par["max_recon_rel_diff"] = worst_recon
+    par["ok"] = bool(worst_code >= 0.999 and worst_recon <= 1e-3)
+    return ref, par
+
+
+def sharded_parity_leg(torch, dist, tq100, args, ctx, order, lins, w_last, acts, sharded_out, sharded_layer):
+    """N > 1: the sharded run's results of the last timed layer against the plain single-GPU path on the same inputs --
+    every rank all-reduces the local Hessians of one whole-owner linear (o_proj) and of down_proj (split by rows from 4
+    GPUs up), quantises them with the single-GPU GPTQ and compares ITS part of the sharded output; minima over ranks."""
+    from tq100.pipeline import LinearView
+    from tq100.gptq import GPTQ, HessianState
+    dev = ctx.device
+    rep = {"against": "single-GPU GPTQ.quantize on the all-reduced Hessian, same weights", "linears": {}}
+    for name in ("o_proj", "down_proj"):
+        i = [l[0] for l in lins].index(name)
+        _, n, m, src = lins[i]
+        st = HessianState(m, dev)
+        st.add_batch(acts[src])
+        H = st.full()
+        dist.all_reduce(H)
+        cnt = torch.tensor([st.nsamples], dtype=torch.int64, device=dev)
+        dist.all_reduce(cnt)
+        st.nsamples = int(cnt.item())
+        st._cache.clear()
+        g = GPTQ(LinearView(w_last[name]), 128, 0.01, hessian=st)
+        g.quantize(use_ssr=order == "ssr", order=order)
+        _, a, u, T8, perm, (lo, hi) = sharded_out[i]
+        stats = torch.tensor([1.0, 1.0, 0.0, 0.0], dtype=torch.float64, device=dev)   # min code, perm equal, max alpha err, rows
+        if a is not None and hi > lo:
+            same = (T8 == g.T_int8[lo:hi])
+            pe = bool(torch.equal(perm.long(), g.perm.long()))
+            clean = same.all(dim=1)
+            aerr = ((a.float() - g.alpha[lo:hi].float()).abs() / g.alpha[lo:hi].float().abs().clamp(min=1e-12))[clean]
+            stats = torch.tensor([float(same.float().mean()), 1.0 if pe else 0.0,
+                                  float(aerr.max()) if aerr.numel() else 0.0, float(hi - lo)], dtype=torch.float64, device=dev)
+        mn = stats.clone()
+        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        rep["linears"][name] = {"shape": [n, m], "min_code_agreement_over_ranks": float(mn[0]), "perm_equal_on_every_rank": bool(mn[1] == 1.0),
+                                "max_alpha_rel_err_on_rows_with_equal_codes": float(mx[2]), "rows_compared": int(sm[3]),
+                                "split_by_rows": bool(sharded_layer.mode == "rows" or
+                                                      sharded_layer.owners([(a_, b_) for _, a_, b_, _ in lins])[i] < 0)}
+    rep["ok"] = all(v["min_code_agreement_over_ranks"] >= 0.999 for v in rep["linears"].values())
+    return rep
 
 
 # ------------------------------------------------------------------------------------ N2 leg
@@ -237,7 +509,9 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--layers", type=int, default=LLAMA2_7B["layers"], help="(debug) fewer layers; the line says so")
+    ap.add_argument("--config", default="7b-ssr", choices=["7b-ssr", "13b-actorder", "layer-sweep"],
+                    help="7b-ssr = BASELINE configs[1] (the driver's line); 13b-actorder = configs[3]; layer-sweep = configs[4]")
+    ap.add_argument("--layers", type=int, default=0, help="(debug) fewer layers; the line says so")
     ap.add_argument("--streams", type=int, default=4, help="CUDA streams the per-linear prologue+sweep chains are spread over")
     ap.add_argument("--shard-mode", default="linears", choices=["linears", "rows"],
                     help="N > 1: deal whole linears to ranks (default) or row-shard every linear (SSR statistics all-reduced)")
@@ -245,6 +519,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-shared", action="store_true", help="skip the secondary shared-Hessian (N1) measurement")
     ap.add_argument("--no-packed", action="store_true", help="skip the secondary packed-layer (N2) measurement")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip the same-box reference-on-CUDA leg (and the parity it feeds)")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", 0))
@@ -252,6 +528,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.config == "layer-sweep":
+        if rank == 0:
+            layer_sweep_line(args)
         return
 
     import torch
@@ -268,7 +548,9 @@ def main():
     from tq100.pipeline import HostPipeline, LinearView
     ctx = par.ShardContext(rank, world, dev)
 
-    cfg = dict(LLAMA2_7B, layers=args.layers)
+    cfg, order = bench_config(args)
+    full_layers = (LLAMA2_13B if args.config == "13b-actorder" else LLAMA2_7B)["layers"]
+    use_ssr = order == "ssr"
     lins = linears(cfg)
     nt = SAMPLES * SEQ
 
@@ -310,14 +592,14 @@ def main():
             if world > 1:
                 # per layer: local Hessians -> NCCL all-reduce -> inverses dealt to ranks + broadcast -> row-slab sweeps
                 results_keep["last"] = sharded_layer.quantize(
-                    [(name, weights[li][name], acts[src]) for name, n, m, src in lins], use_ssr=True,
+                    [(name, weights[li][name], acts[src]) for name, n, m, src in lins], use_ssr=use_ssr, order=order,
                     hess_timing=hess_events if record else None)
                 continue
             if os.environ.get("BENCH_DEBUG"):
                 torch.cuda.synchronize()
                 t_dbg = time.perf_counter()
             results_keep["last"] = driver.quantize(
-                [(name, weights[li][name], acts[src]) for name, n, m, src in lins], use_ssr=True,
+                [(name, weights[li][name], acts[src]) for name, n, m, src in lins], use_ssr=use_ssr, order=order,
                 hess_timing=hess_events if record else None)
             if os.environ.get("BENCH_DEBUG"):
                 torch.cuda.synchronize()
@@ -367,7 +649,7 @@ def main():
     achieved = flops / (h_ms * 1e-3) / 1e12 if h_ms > 0 else 0.0
     # DRAM traffic per launch from the committed ncu --set full capture (profiles/r01c_ncu_full_hessian_tc.txt:
     # dram__bytes_read.sum + dram__bytes_write.sum), averaged over the launches of one layer like `achieved`
-    NCU_TRAFFIC = {4096: 4.56e9, 11008: 45.6e9}            # bytes per launch at Nt = 262144, by m
+    NCU_TRAFFIC = {4096: 4.56e9, 11008: 45.6e9} if world == 1 else {}   # bytes per launch at Nt = 262144, by m
     known = [NCU_TRAFFIC[m_] for _, _, t_, m_ in hess_events if m_ in NCU_TRAFFIC and t_ == SAMPLES * SEQ]
     traffic = sum(known) / len(known) if known and len(known) == len(hess_events) else None
     roofline = {"kernel": "hessian_tc_kernel", "bound": "tensor", "achieved": achieved, "peak": peak,
@@ -390,7 +672,7 @@ def main():
         def quantize_model_shared():
             for li in range(cfg["layers"]):
                 results_keep["last"] = shared_driver.quantize(
-                    [(name, weights[li][name], acts[src]) for name, n, m, src in lins], use_ssr=True)
+                    [(name, weights[li][name], acts[src]) for name, n, m, src in lins], use_ssr=use_ssr, order=order)
 
         quantize_model_shared()
         torch.cuda.synchronize()
@@ -411,10 +693,9 @@ def main():
         # one layer's weights and the four calibration inputs in pinned host memory, streamed per layer
         host_acts = {k: v.reshape(-1, v.shape[-1]).cpu().pin_memory() for k, v in acts.items()}
         host_w = {name: weights[0][name].cpu().pin_memory() for name, _, _, _ in lins}
-        order = ["attn_in", "o_in", "mlp_in", "down_in"]
         groups_one_layer = [(host_acts[k], [(name, host_w[name]) for name, _, _, src in lins if src == k])
-                            for k in order]
-        pipe = HostPipeline(dev, block_size=128, percdamp=0.01, use_ssr=True, aga="hessian")
+                            for k in ("attn_in", "o_in", "mlp_in", "down_in")]
+        pipe = HostPipeline(dev, block_size=128, percdamp=0.01, use_ssr=use_ssr, aga="hessian", order=order)
         pipe.run(groups_one_layer)                                 # warm-up (allocations, pinned outputs)
         torch.cuda.synchronize()
         pipe.h2d_bytes = pipe.d2h_bytes = 0
@@ -432,7 +713,7 @@ def main():
                "note": "HostPipeline.run per layer: each of the layer's 4 distinct calibration inputs and 7 weights "
                        "copied from pinned host memory on a side stream (double-buffered: the next input's copy is "
                        "enqueued before this input's kernels), alpha/mu/T(int8)/perm copied back to pinned host memory; "
-                       "wall clock around all 32 layers"}
+                       "wall clock around all layers"}
         del host_acts, host_w, pipe, res
     elif not args.no_e2e:
         # N > 1: every rank streams ITS calibration samples and ITS row slab of the weights from pinned host memory,
@@ -448,8 +729,8 @@ def main():
         host_w = {name: (weights[0][name][slabs[name][0]:slabs[name][1]].cpu().pin_memory() if slabs[name] else None)
                   for name, _, _, _ in lins}
         one_layer = (host_acts, [(name, host_w[name], n, src) for name, n, m, src in lins])
-        spipe = par.ShardedHostPipeline(ctx, block_size=128, percdamp=0.01, use_ssr=True, aga="hessian",
-                                        mode=args.shard_mode)
+        spipe = par.ShardedHostPipeline(ctx, block_size=128, percdamp=0.01, use_ssr=use_ssr, aga="hessian",
+                                        mode=args.shard_mode, order=order)
         for keep in spipe.run_iter([one_layer]):                   # warm-up (device slots, pinned outputs)
             pass
         spipe.synchronize()
@@ -471,6 +752,23 @@ def main():
         t = torch.tensor([e2e["value"]], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e["value"] = float(t.item())
+    # ---- same-box bar: the reference's own code path with device='cuda' (its default
+    # device, main.py:368), fp32, TF32 off, on ONE transformer layer with all 262144 tokens -- cuBLAS sgemm, cuSOLVER
+    # potrf/potri and the reference's per-iteration host syncs -- times the layer count.  Its outputs on layer 0 are also
+    # the yardstick of `parity`: the timed run's own layer-0 results against them, linear by linear.
+    ref_cuda = parity = None
+    if world == 1 and not args.no_ref_cuda:
+        try:
+            ref_cuda, parity = reference_cuda_leg(torch, args, cfg, order, lins, weights[0], acts, driver, dev)
+        except Exception as exc:
+            ref_cuda = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    elif world > 1 and not args.no_parity:
+        try:
+            parity = sharded_parity_leg(torch, dist, tq100, args, ctx, order, lins, weights[cfg["layers"] - 1], acts,
+                                        results_keep["last"], sharded_layer)
+        except Exception as exc:
+            parity = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     # ---- SURVEY 8(f) N2, reported beside the headline: the packed inference layer on the codes (TernaryLinear):
     # one 4096x4096 fp16 layer with a random permutation; decode call (1 token, tq_tl_gemv) over layer copies that
     # total > 2x L2, and a 512-token call through tq_tl_gemm_tc vs dense weight + library GEMM.  Device-timed replay
@@ -484,20 +782,29 @@ def main():
             n2 = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     if rank == 0:
-        line = {"metric": "LLaMA-2-7B ternary PTQ wall-time", "value": value, "unit": "s", "n_gpus": world,
+        line = {"metric": METRIC[args.config], "value": value, "unit": "s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": workload_config(args), "clocks": clocks,
                 "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e}
-        if args.layers != LLAMA2_7B["layers"]:
-            line["config"]["workload"] += f" [DEBUG: only {args.layers} of 32 layers]"
+        if cfg["layers"] != full_layers:
+            line["config"]["workload"] += f" [DEBUG: only {cfg['layers']} of {full_layers} layers]"
         if n1 is not None:
             line["n1_shared_inputs"] = n1
         if n2 is not None:
             line["n2_packed_layer"] = n2
         line["dtype_note"] = "fp32 arithmetic; fp16 activations enter the tensor cores exactly, fp32 accumulate"
-        if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_arm()
+        if ref_cuda is not None:
+            line["reference_cuda"] = ref_cuda
+        if parity is not None:
+            line["parity"] = parity
+        if not args.no_cpu_baseline and world == 1:
+            # rank 0 at N = 1 only (at N > 1 the other ranks would spin in the final barrier on the same host cores);
+            # one pass over the layer's 7 linears -- the `--impl reference` arm is the repeated measurement
+            free = torch.cuda.mem_get_info(dev)[0]
+            del acts, weights
+            torch.cuda.empty_cache()
+            line["cpu_baseline"] = cpu_layer_sample(cfg, order, steps=1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -25,13 +25,18 @@ def _round(W, alpha, mu):
 def atq_block(W, gram_in=None, gram=None, max_iter=100, margin_out=None):
     """init (quantizer.py:49-67) -> ITF with the global stop test (:160-175) -> AGA (:207-246).
     gram_in: matrix handed to AGA as 'X' (S = X'X); gram: S itself.
-    margin_out (adjudication aid): a one-element list that receives | |Z| - 0.5 | of the rounding that
-    produced the returned T, i.e. how far every code sits from a threshold tie."""
+    margin_out (adjudication aid): a list that receives (final, trajectory): ``final`` (n, b) is
+    | |Z| - 0.5 | of the rounding that produced the returned T; ``trajectory`` (n,) is the smallest such margin the row
+    met at ANY rounding on the way (the init threshold | |Wc| / (2 delta) - 0.5 | included) -- ITF can be tipped into a
+    different fixed point by a tie several iterations before the last one."""
     mu = W.mean(1, keepdim=True)
     Wc = W - mu
     delta = 0.75 * Wc.abs().mean(1, keepdim=True)
     T = (Wc > delta).to(W.dtype) - (Wc < -delta).to(W.dtype)
     alpha = (T * Wc).sum(1, True) / T.abs().sum(1, True).clamp(min=_TINY)
+    traj = None
+    if margin_out is not None:
+        traj = (0.5 * Wc.abs() / delta.clamp(min=_TINY) - 0.5).abs().amin(1)
     T_prev = torch.zeros_like(T)
     for _ in range(max_iter):
         if torch.equal(T, T_prev):
@@ -39,8 +44,11 @@ def atq_block(W, gram_in=None, gram=None, max_iter=100, margin_out=None):
         T_prev = T
         alpha, mu = _grid(W, T)
         T = _round(W, alpha, mu)
+        if traj is not None:
+            traj = torch.minimum(traj, (((W - mu) / alpha.clamp(min=_TINY)).abs() - 0.5).abs().amin(1))
     if margin_out is not None:
         margin_out.append((((W - mu) / alpha.clamp(min=_TINY)).abs() - 0.5).abs())
+        margin_out.append(traj)
     S = gram if gram is not None else (gram_in.T @ gram_in if gram_in is not None else None)
     if S is not None:
         s1 = S.sum(1, keepdim=True)                                 # S @ 1
@@ -51,13 +59,21 @@ def atq_block(W, gram_in=None, gram=None, max_iter=100, margin_out=None):
     return alpha, mu, T
 
 
-def ssr_select(W, remaining, block):
+def ssr_select(W, remaining, block, gap_out=None):
+    """gap_out (adjudication aid): a list that receives the similarity gap between the last column taken
+    and the best column left out -- a top-k boundary closer than the fp32 noise of the similarities may legitimately
+    fall the other way."""
     if remaining.numel() <= block:                                  # reorder.py:125-126
+        if gap_out is not None:
+            gap_out.append(float("inf"))
         return remaining, remaining[:0]
     Wr = W[:, remaining]
     wm = Wr.mean(1, keepdim=True)
     sim = ((Wr / Wr.norm(dim=0, keepdim=True).clamp(min=_TINY)).T @ (wm / wm.norm().clamp(min=_TINY))).squeeze(1)
     top = torch.topk(sim, block).indices                            # reorder.py:133
+    if gap_out is not None:
+        two = torch.topk(sim, block + 1).values
+        gap_out.append(float(two[block - 1] - two[block]))
     keep = torch.ones(remaining.numel(), dtype=torch.bool, device=remaining.device)
     keep[top] = False
     return remaining[top], remaining[keep]
@@ -83,7 +99,9 @@ def quantize_layer(W, Hraw, nsamples, block=128, percdamp=0.01, use_ssr=True, ag
     """gptq.py:78-199 on W's device and dtype (CPU fp32 = the reference's CPU path; a CUDA tensor runs the same ATen
     calls on the GPU, the reference's own default device, main.py:368).  static_perm: a fixed sweep order (the
     act-order extension: the reference with use_ssr=False on pre-permuted columns).  return_margin adds a
-    fifth output: | |Z| - 0.5 | per code, in original column positions."""
+    fifth output, the adjudication aids of SURVEY 8c: {'final': | |Z| - 0.5 | per code in original column positions,
+    'trajectory': (n, nb) smallest margin each row met at any rounding of the block, 'topk_gap': per block, the
+    similarity gap at the SSR top-k boundary}."""
     W = W.clone()
     n, m = W.shape
     dev = W.device
@@ -91,12 +109,13 @@ def quantize_layer(W, Hraw, nsamples, block=128, percdamp=0.01, use_ssr=True, ag
     dinv = torch.diag(Hinv).clamp(min=_TINY)
     T_full = torch.zeros_like(W)
     margin = torch.zeros_like(W) if return_margin else None
+    traj, gaps = [], ([] if return_margin else None)
     alphas, mus, perm = [], [], []
     remaining = torch.arange(m, device=dev)
     done = 0
     while done < m:
         if use_ssr:
-            blk, remaining = ssr_select(W, remaining, block)
+            blk, remaining = ssr_select(W, remaining, block, gap_out=gaps)
             rem = remaining
         elif static_perm is not None:
             hi = min(done + block, m)
@@ -115,6 +134,7 @@ def quantize_layer(W, Hraw, nsamples, block=128, percdamp=0.01, use_ssr=True, ag
             a, u, Tb = atq_block(Wb, max_iter=max_iter, margin_out=mo)
         if return_margin:
             margin[:, blk] = mo[0]
+            traj.append(mo[1])
         alphas.append(a)
         mus.append(u)
         T_full[:, blk] = Tb
@@ -123,4 +143,6 @@ def quantize_layer(W, Hraw, nsamples, block=128, percdamp=0.01, use_ssr=True, ag
             W[:, rem] -= E @ (Hinv[blk][:, rem] / dinv[blk][:, None])   # gptq.py:173-186
         done += blk.numel()
     out = (torch.cat(alphas, 1), torch.cat(mus, 1), T_full, torch.cat(perm))
-    return out + (margin,) if return_margin else out
+    if return_margin:
+        return out + ({"final": margin, "trajectory": torch.stack(traj, 1), "topk_gap": gaps if use_ssr else None},)
+    return out

@@ -2,7 +2,15 @@
 inference layer (model.py) and its whole-model driver (main.py) over hand-written sm_100a CUDA kernels behind a C ABI
 (include/tq100.h, libtq100.so)."""
 
-from . import _lib  # noqa: F401
+import os as _os
+
+# The chains of a layer's linears run on many CUDA streams (seven chains, each with two helper streams inside the
+# inverse).  With the default of 8 hardware work queues, streams alias onto the same queue and serialise falsely (measured:
+# 135 -> 126 ms per 7B layer with 32).  Read by the driver when the CUDA context is created, so it only takes effect if this
+# package is imported before the first CUDA call; an explicit user setting wins.
+_os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
+from . import _lib  # noqa: E402,F401
 from .quantizer import (  # noqa: F401
     AsymmetricTernaryQuantizer,
     compute_quantization_error,

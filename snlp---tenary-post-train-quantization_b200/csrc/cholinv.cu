@@ -370,10 +370,14 @@ static ChainStreams helper_streams_for(cudaStream_t st) {
     auto it = pool.find(st);
     if (it != pool.end()) return it->second;
     ChainStreams cs;
-    int lo = 0, hi = 0;
+    int lo = 0, hi = 0, mine = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);                 // lo = least priority (numerically greatest)
-    if (cudaStreamCreateWithFlags(&cs.aux, cudaStreamNonBlocking) != cudaSuccess) cs.aux = nullptr;
-    if (cudaStreamCreateWithPriority(&cs.bulk, cudaStreamNonBlocking, lo) != cudaSuccess) cs.bulk = nullptr;
+    // the helpers follow the caller's priority: a chain that was placed above the Hessian stream must not have half of
+    // its inverse queue behind the Hessian's CTAs; `bulk` sits one level below its chain (but not below other chains' aux)
+    if (cudaStreamGetPriority(st, &mine) != cudaSuccess) mine = lo;
+    const int bulk_prio = (mine + 1 <= lo) ? mine + 1 : lo;
+    if (cudaStreamCreateWithPriority(&cs.aux, cudaStreamNonBlocking, mine) != cudaSuccess) cs.aux = nullptr;
+    if (cudaStreamCreateWithPriority(&cs.bulk, cudaStreamNonBlocking, bulk_prio) != cudaSuccess) cs.bulk = nullptr;
     pool[st] = cs;
     return cs;
 }
@@ -420,6 +424,9 @@ extern "C" int tq_chol_inverse(float* Hinv, const float* Hd, int64_t m, float* w
     int rc;
     // operand descriptors, encoded once per inversion over the whole stacked / strip arrays
     GemmOperands ops_potrf, ops_trtri;
+    GemmC c_L, c_X;                            // output matrices of the tensor-core updates (TMA reduce-add epilogue)
+    if ((rc = gemm_cmap_encode(&c_L, L, m, m, ld))) return rc;
+    if ((rc = gemm_cmap_encode(&c_X, X, m, m, ld))) return rc;
     if (panels > 1) {
         if (tc_potrf && (rc = gemm_operands_encode(&ops_potrf, Sh, Sl, CB, srows, Sh, Sl, CB, srows, CB))) return rc;
         if (tc_trtri && (rc = gemm_operands_encode(&ops_trtri, Sh, Sl, CB, srows, Bh, Bl, CB, mp, CB))) return rc;
@@ -474,23 +481,21 @@ extern "C" int tq_chol_inverse(float* Hinv, const float* Hd, int64_t m, float* w
                 // (a) column panel k+1 on `st` -- it also receives the bulk of update k-1, so join that first
                 if (bulk_pending) TQ_CUDA(cudaStreamWaitEvent(st, chol_event(3 * (k - 1) + 2), 0));
                 const int64_t la = below < CB ? below : CB;
-                if ((rc = launch_gemm_tf32x3_rows(GX_SUB_LOWER, L + (int64_t)(k0 + CB) * ld + (k0 + CB), ld, below, la,
-                                                  &ops_potrf, off, off, nullptr, 0, st)))
+                if ((rc = launch_gemm_tf32x3_at(GX_SUB_LOWER, &c_L, k0 + CB, k0 + CB, below, la, &ops_potrf, off, off, st)))
                     return rc;
                 bulk_pending = false;
                 // (b) the remaining columns on `bulk`, released only after (a) so the short look-ahead GEMM gets the SMs
                 if (below > CB) {
                     TQ_CUDA(cudaEventRecord(chol_event(3 * k + 1), st));
                     TQ_CUDA(cudaStreamWaitEvent(bulk, chol_event(3 * k + 1), 0));
-                    if ((rc = launch_gemm_tf32x3_rows(GX_SUB_LOWER, L + (int64_t)(k0 + 2 * CB) * ld + (k0 + 2 * CB), ld,
-                                                      below - CB, below - CB, &ops_potrf, off + CB, off + CB, nullptr, 0, bulk)))
+                    if ((rc = launch_gemm_tf32x3_at(GX_SUB_LOWER, &c_L, k0 + 2 * CB, k0 + 2 * CB, below - CB, below - CB,
+                                                    &ops_potrf, off + CB, off + CB, bulk)))
                         return rc;
                     TQ_CUDA(cudaEventRecord(chol_event(3 * k + 2), bulk));
                     bulk_pending = true;
                 }
             } else if (tc_potrf) {
-                if ((rc = launch_gemm_tf32x3_rows(GX_SUB_LOWER, L + (int64_t)(k0 + CB) * ld + (k0 + CB), ld, below, below,
-                                                  &ops_potrf, off, off, nullptr, 0, st)))
+                if ((rc = launch_gemm_tf32x3_at(GX_SUB_LOWER, &c_L, k0 + CB, k0 + CB, below, below, &ops_potrf, off, off, st)))
                     return rc;
             } else {
                 const int tiles = (int)ceil_div(below, GT_M);
@@ -507,8 +512,7 @@ extern "C" int tq_chol_inverse(float* Hinv, const float* Hd, int64_t m, float* w
                 // R_i,: -= L_ik X_k,: : A = stacked split of the L panel, B = the just-finished strip X_k,: transposed
                 const int64_t cend = k0 + nb;
                 if ((rc = launch_split(X + (int64_t)k0 * ld, ld, nb, cend, Bh, Bl, CB, 1, s2))) return rc;
-                if ((rc = launch_gemm_tf32x3_rows(GX_SUB_RECT, X + (int64_t)(k0 + CB) * ld, ld, below, cend, &ops_trtri, off, 0,
-                                                  nullptr, 0, s2)))
+                if ((rc = launch_gemm_tf32x3_at(GX_SUB_RECT, &c_X, k0 + CB, 0, below, cend, &ops_trtri, off, 0, s2)))
                     return rc;
             } else {
                 trtri_update_kernel<<<dim3(ctiles, (unsigned)ceil_div(below, GT_M)), GT_THREADS, 0, s2>>>(X, ld, L, ld, M, k0);
@@ -529,7 +533,9 @@ extern "C" int tq_chol_inverse(float* Hinv, const float* Hd, int64_t m, float* w
         // starts at the tile's first column because Y[i][q] = 0 for q < i
         float *Yh = S, *Yl = S + m * m;
         if ((rc = launch_split(X, ld, m, m, Yh, Yl, m, 1, st))) return rc;
-        if ((rc = launch_gemm_tf32x3(GX_STORE_UPPER, Hinv, ld, m, m, m, Yh, Yl, m, Yh, Yl, m, nullptr, 0, st))) return rc;
+        GemmOperands ops_lauum;
+        if ((rc = gemm_operands_encode(&ops_lauum, Yh, Yl, m, m, Yh, Yl, m, m, m))) return rc;
+        if ((rc = launch_gemm_tf32x3_at(GX_STORE_UPPER, &c_L, 0, 0, m, m, &ops_lauum, 0, 0, st))) return rc;
     } else {
         const int nt = (int)ceil_div(m, GT_M);
         lauum_kernel<<<dim3(nt, nt), GT_THREADS, 0, st>>>(Hinv, ld, X, ld, M);

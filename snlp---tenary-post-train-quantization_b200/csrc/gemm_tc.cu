@@ -21,14 +21,19 @@
 
 namespace tq {
 
-constexpr int GX_BM = 128, GX_BN = 128, GX_BK = 32, GX_STAGES = 2, GX_UMMA_K = 8;
+constexpr int GX_BM = 128, GX_BN = 128, GX_BK = 32, GX_UMMA_K = 8;
+constexpr int GX_STAGES_RMW = 2;                     // epilogue = read-modify-write through a shared-memory C tile
+constexpr int GX_STAGES_TMA = 3;                     // epilogue = TMA store / reduce-add from two 16 KB staging slabs
 constexpr int GX_SLAB = GX_BM * GX_BK * 4;            // 16384
 constexpr int GX_STAGE_BYTES = 4 * GX_SLAB;           // 65536
 constexpr int GX_THREADS = 384;                 // 4 control warps + 8 epilogue warps
 constexpr int GX_EPI_WARPS = 8;
 constexpr int GX_CT_LD = GX_BN + 1;                // pitch of the C tile in shared memory (bank-conflict-free both ways)
 constexpr int GX_COLPART = 2 * GX_EPI_WARPS * 64 * 2 * 4;   // double-buffered per-warp column partials (dot, sq)
-constexpr int GX_SMEM = GX_STAGES * GX_STAGE_BYTES + 256 + GX_BM * GX_CT_LD * 4 + GX_COLPART + 1024;   // stages, barriers, C tile, slack   // stages, barriers, epilogue staging, alignment slack
+constexpr int GX_SMEM = GX_STAGES_RMW * GX_STAGE_BYTES + 256 + GX_BM * GX_CT_LD * 4 + GX_COLPART + 1024;   // stages, barriers, C tile, slack
+constexpr int GX_EPI_COLS = 32;                      // one TMA box of C: 128 rows x 32 columns (128-byte swizzled rows)
+constexpr int GX_EPI_BYTES = GX_BM * GX_EPI_COLS * 4;                                             // 16384
+constexpr int GX_SMEM_TMA = GX_STAGES_TMA * GX_STAGE_BYTES + 2 * GX_EPI_BYTES + 256 + 1024;       // stages, staging, barriers, slack
 constexpr int GX_TMEM_COLS = 256;
 
 struct GxProblem {
@@ -49,6 +54,8 @@ struct GxProblem {
     int k_chunk;            // > 0: TMEM accumulates at most k_chunk of K at a time; chunks are summed in the
                             // smem C tile with round-to-nearest fp32 adds (the tensor core's accumulate truncates)
     int debug;              // development switch (env TQ_GX_DEBUG): 1 = drain accumulators only, 2 = no prefetch loads
+    int c_row0, c_col0;     // TMA epilogue: coordinates of C[0, 0] inside the matrix the C descriptor was encoded over
+    int skip_lolo;          // 1: three products (lo*hi' + hi*lo' + hi*hi'); the lo*lo' term is ~2^-22 of the product
 };
 
 __device__ __forceinline__ void gx_decode(const GxProblem& p, int t, int& bi, int& bj) {
@@ -81,19 +88,28 @@ __device__ __forceinline__ uint64_t gx_desc(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// TMA_EPI = false: the epilogue reads C into shared memory, subtracts, writes back (needed when the columns of C are
+//   gathered through col_idx, or when the updated values feed the SSR statistics).
+// TMA_EPI = true : C is a plain tile of a matrix described by map_c.  The SMs never read it: the negated accumulator
+//   goes TMEM -> registers -> swizzled staging slab -> TMA reduce-add, i.e. the fp32 add `C + (-acc)` is performed by
+//   the L2 (round-to-nearest: bit-identical to the subtraction the other path does); GX_STORE_UPPER stores the first K
+//   chunk and reduce-adds the later ones.  The shared memory the C tile no longer needs holds a third pipeline stage.
+template <bool TMA_EPI>
 __global__ void __launch_bounds__(GX_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_constant__ CUtensorMap map_al,
                    const __grid_constant__ CUtensorMap map_bh, const __grid_constant__ CUtensorMap map_bl,
-                   const GxProblem p) {
+                   const __grid_constant__ CUtensorMap map_c, const GxProblem p) {
+    constexpr int GX_STAGES = TMA_EPI ? GX_STAGES_TMA : GX_STAGES_RMW;
+    constexpr int GX_BAR_OFF = GX_STAGES * GX_STAGE_BYTES + (TMA_EPI ? 2 * GX_EPI_BYTES : 0);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t s_base = smem_u32(smem);
-    const uint32_t s_bar = s_base + GX_STAGES * GX_STAGE_BYTES;
+    const uint32_t s_bar = s_base + GX_BAR_OFF;
     auto full_bar = [&](int s) { return s_bar + 8 * s; };
     auto empty_bar = [&](int s) { return s_bar + 8 * (GX_STAGES + s); };
     auto tfull_bar = [&](int a) { return s_bar + 8 * (2 * GX_STAGES + a); };
     auto tempty_bar = [&](int a) { return s_bar + 8 * (2 * GX_STAGES + 2 + a); };
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + GX_STAGES * GX_STAGE_BYTES + 8 * (2 * GX_STAGES + 4));
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + GX_BAR_OFF + 8 * (2 * GX_STAGES + 4));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -101,6 +117,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_al) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bh) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bl) : "memory");
+        if (TMA_EPI) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < GX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -159,9 +176,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
                         const uint32_t off = kk * GX_UMMA_K * 4;             // 32 bytes along K inside the swizzled row
                         const uint64_t ah = gx_desc(s0 + 0 * GX_SLAB + off), al = gx_desc(s0 + 1 * GX_SLAB + off);
                         const uint64_t bh = gx_desc(s0 + 2 * GX_SLAB + off), bl = gx_desc(s0 + 3 * GX_SLAB + off);
-                        umma_tf32(tmem_d, al, bl, idesc, first ? 0u : 1u);     // smallest term first
+                        if (!p.skip_lolo) {
+                            umma_tf32(tmem_d, al, bl, idesc, first ? 0u : 1u);     // smallest term first
+                            first = false;
+                        }
+                        umma_tf32(tmem_d, al, bh, idesc, first ? 0u : 1u);
                         first = false;
-                        umma_tf32(tmem_d, al, bh, idesc, 1u);
                         umma_tf32(tmem_d, ah, bl, idesc, 1u);
                         umma_tf32(tmem_d, ah, bh, idesc, 1u);
                     }
@@ -171,7 +191,78 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
                 }
             }
         }
-    } else if (warp >= 4) {
+    } else if (TMA_EPI && warp >= 4) {
+        // ===== epilogue through TMA.  Eight warps: warp % 4 is the TMEM lane quarter (32 rows), (warp - 4) / 4 the half of
+        // the tile's columns; each half owns one 16 KB staging slab (128 rows x 32 columns, 128B-swizzled like the box of
+        // map_c) and walks its two 32-column groups: tcgen05.ld -> negate / mask -> st.shared -> one elected thread issues
+        // the bulk tensor reduce-add.  Nothing of C is read by the SM.
+        const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const int row = q * 32 + lane;
+        const bool leader = (q == 0 && lane == 0);
+        const uint32_t s_stage = s_base + GX_STAGES * GX_STAGE_BYTES + half * GX_EPI_BYTES;
+        const bool store_mode = (p.mode == GX_STORE_UPPER);
+        const bool lower = (p.mode == GX_SUB_LOWER);
+        int n_item = 0;
+        for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+            int bi, bj;
+            gx_decode(p, t, bi, bj);
+            const int r_loc = bi * GX_BM + row;
+            const bool row_ok = r_loc < p.M;
+            const int kb0 = k_begin_of(bj);
+            const int kc = (p.k_chunk > 0) ? p.k_chunk : p.K;
+            bool first_chunk = true;
+            for (int c0 = kb0; c0 < p.K; c0 += kc, ++n_item) {
+                const int acc = n_item & 1;
+                mbar_wait(tfull_bar(acc), (n_item >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int cgi = 0; cgi < 2; ++cgi) {
+                    const int cg = half * 2 + cgi;
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * GX_BN + cg * GX_EPI_COLS, v);
+                    tmem_ld_wait();
+                    if (cgi == 1) {
+                        tc_fence_before();
+                        mbar_arrive(tempty_bar(acc));
+                    }
+                    const int j0 = bj * GX_BN + cg * GX_EPI_COLS;
+                    const bool diag_tile = lower && bi == bj;
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const int j = j0 + c;
+                        const bool ok = row_ok && j < p.N && (!diag_tile || j <= r_loc);
+                        const float a = __uint_as_float(v[c]);
+                        v[c] = __float_as_uint(ok ? (store_mode ? a : -a) : 0.f);
+                    }
+                    // this half's previous bulk operation must have read the slab (and, when chunks of one tile are
+                    // stored then added, must have completed) before the slab is rewritten
+                    if (leader) {
+                        if (store_mode) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                        else bulk_wait_read<0>();
+                    }
+                    named_bar_sync(1 + half, 128);
+                    const uint32_t sdst = s_stage + row * 128;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint32_t a = sdst + ((c ^ (row & 7)) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * c]), "r"(v[4 * c + 1]),
+                                     "r"(v[4 * c + 2]), "r"(v[4 * c + 3])
+                                     : "memory");
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(1 + half, 128);
+                    if (leader) {
+                        if (store_mode && first_chunk) tma_store_2d(&map_c, s_stage, p.c_col0 + j0, p.c_row0 + bi * GX_BM);
+                        else tma_reduce_add_2d(&map_c, s_stage, p.c_col0 + j0, p.c_row0 + bi * GX_BM);
+                        bulk_commit();
+                    }
+                }
+                first_chunk = false;
+            }
+        }
+        if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    } else if (!TMA_EPI && warp >= 4) {
         // ===== epilogue: read-modify-write of the C tile through shared memory.
         // Eight warps; warp % 4 is the TMEM lane quarter (32 rows), (warp - 4) / 4 the half of the tile's columns.
         //  1. BEFORE the accumulator is awaited, the old values of the warp's 32 x 64 block of C are fetched with
@@ -184,7 +275,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_ah, const __grid_cons
         const int q = warp & 3;
         const int half = (warp - 4) >> 2;
         constexpr int NCG = GX_BN / 64;                          // column groups of 32 per warp
-        float* ctile = reinterpret_cast<float*>(smem + GX_STAGES * GX_STAGE_BYTES + 256);
+        float* ctile = reinterpret_cast<float*>(smem + GX_BAR_OFF + 256);
         float* cw = ctile + (q * 32) * GX_CT_LD + half * 64;    // this warp's 32 x 64 block
         const bool rmw = (p.mode != GX_STORE_UPPER) && p.debug != 2;
         const bool lower = (p.mode == GX_SUB_LOWER);
@@ -426,6 +517,21 @@ int gemm_operands_encode(GemmOperands* ops, const float* Ah, const float* Al, in
     return 0;
 }
 
+// TMA descriptor of a whole output matrix (box 128 rows x 32 columns) for the TMA epilogue; `valid` stays false when
+// the matrix cannot be described (base not 16-byte aligned, row pitch not a multiple of 16 bytes): callers then get the
+// read-modify-write epilogue.
+int gemm_cmap_encode(GemmC* c, float* base, int64_t rows, int64_t cols, int64_t ld) {
+    c->valid = false;
+    c->base = base;
+    c->ld = ld;
+    static const bool off = []() { const char* e = getenv("TQ_GX_NO_TMA_EPI"); return e && atoi(e) != 0; }();
+    if (off || (ld % 4) != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return 0;
+    int rc = make_tmap_2d(&c->map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, rows, cols, ld, GX_BM, GX_EPI_COLS, "gemm_tf32x3(C)");
+    if (rc) return rc;
+    c->valid = true;
+    return 0;
+}
+
 // C (op)= A B' with pre-encoded operands; M, N <= the extents the operands were encoded with
 int launch_gemm_tf32x3_ops(int mode, float* C, int64_t ldc, int64_t M, int64_t N, const GemmOperands* ops,
                            const int32_t* col_idx, int64_t col0, cudaStream_t st) {
@@ -435,22 +541,31 @@ int launch_gemm_tf32x3_ops(int mode, float* C, int64_t ldc, int64_t M, int64_t N
 // as above, with A and B starting at rows a_row0 / b_row0 of the arrays the descriptors describe
 static int launch_gemm_impl(int mode, float* C, int64_t ldc, int64_t M, int64_t N, const GemmOperands* ops, int64_t a_row0,
                             int64_t b_row0, const int32_t* col_idx, int64_t col0, const float* wbar, float* stat_partials,
-                            float* rowsum_part, cudaStream_t st);
+                            float* rowsum_part, const GemmC* cmap, int64_t c_row0, int64_t c_col0, cudaStream_t st);
 
 int launch_gemm_tf32x3_rows(int mode, float* C, int64_t ldc, int64_t M, int64_t N, const GemmOperands* ops,
                             int64_t a_row0, int64_t b_row0, const int32_t* col_idx, int64_t col0, cudaStream_t st) {
-    return launch_gemm_impl(mode, C, ldc, M, N, ops, a_row0, b_row0, col_idx, col0, nullptr, nullptr, nullptr, st);
+    return launch_gemm_impl(mode, C, ldc, M, N, ops, a_row0, b_row0, col_idx, col0, nullptr, nullptr, nullptr, nullptr, 0, 0, st);
+}
+
+// C = the sub-matrix of `cmap`'s matrix whose first element sits at (c_row0, c_col0); plain (ungathered) columns.
+// Takes the TMA epilogue when the descriptor is valid, else the read-modify-write epilogue on the same addresses.
+int launch_gemm_tf32x3_at(int mode, const GemmC* cmap, int64_t c_row0, int64_t c_col0, int64_t M, int64_t N,
+                          const GemmOperands* ops, int64_t a_row0, int64_t b_row0, cudaStream_t st) {
+    float* C = cmap->base + c_row0 * cmap->ld + c_col0;
+    return launch_gemm_impl(mode, C, cmap->ld, M, N, ops, a_row0, b_row0, nullptr, 0, nullptr, nullptr, nullptr, cmap, c_row0,
+                            c_col0, st);
 }
 
 // error feedback with the next block's SSR statistics emitted from the epilogue
 int launch_gemm_feedback_stats(float* C, int64_t ldc, int64_t M, int64_t N, const GemmOperands* ops, const int32_t* col_idx,
                                int64_t col0, const float* wbar, float* stat_partials, float* rowsum_part, cudaStream_t st) {
-    return launch_gemm_impl(GX_FEEDBACK, C, ldc, M, N, ops, 0, 0, col_idx, col0, wbar, stat_partials, rowsum_part, st);
+    return launch_gemm_impl(GX_FEEDBACK, C, ldc, M, N, ops, 0, 0, col_idx, col0, wbar, stat_partials, rowsum_part, nullptr, 0, 0, st);
 }
 
 static int launch_gemm_impl(int mode, float* C, int64_t ldc, int64_t M, int64_t N, const GemmOperands* ops, int64_t a_row0,
                             int64_t b_row0, const int32_t* col_idx, int64_t col0, const float* wbar, float* stat_partials,
-                            float* rowsum_part, cudaStream_t st) {
+                            float* rowsum_part, const GemmC* cmap, int64_t c_row0, int64_t c_col0, cudaStream_t st) {
     const int64_t K = ops->K;
     if (M <= 0 || N <= 0 || K <= 0) return 0;
     GxProblem p;
@@ -464,6 +579,10 @@ static int launch_gemm_impl(int mode, float* C, int64_t ldc, int64_t M, int64_t 
     p.wbar = wbar; p.stat_partials = stat_partials; p.rowsum_part = rowsum_part;
     static const int dbg = []() { const char* e = getenv("TQ_GX_DEBUG"); return e ? atoi(e) : 0; }();
     p.debug = dbg;
+    p.c_row0 = (int)c_row0; p.c_col0 = (int)c_col0;
+    static const int products = []() { const char* e = getenv("TQ_GX_PRODUCTS"); return e ? atoi(e) : 4; }();
+    p.skip_lolo = (products == 3) ? 1 : 0;
+    const bool tma_epi = cmap != nullptr && cmap->valid && col_idx == nullptr && stat_partials == nullptr && dbg == 0;
     if (mode == GX_SUB_LOWER) {
         p.tiles = 0;
         for (int j = 0; j < p.nt; ++j) p.tiles += (p.mt - j > 0) ? p.mt - j : 0;
@@ -474,10 +593,12 @@ static int launch_gemm_impl(int mode, float* C, int64_t ldc, int64_t M, int64_t 
         p.tiles = p.mt * p.nt;
     }
     if (p.tiles <= 0) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        TQ_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GX_SMEM));
-        attr_set = true;
+    static std::atomic<unsigned long long> attr_mask{0};
+    int dev;
+    if (dyn_smem_pending(attr_mask, dev)) {
+        TQ_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GX_SMEM));
+        TQ_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GX_SMEM_TMA));
+        dyn_smem_done(attr_mask, dev);
     }
     // Persistent CTAs of this kernel fill an SM's shared memory.  The chains of other linears on other streams are made of
     // short one-CTA kernels (diagonal-block factorisation, block selection, ...); a few SMs are left to them so they do
@@ -486,7 +607,10 @@ static int launch_gemm_impl(int mode, float* C, int64_t ldc, int64_t M, int64_t 
     int sms = sm_count() - spare;
     if (sms < 1) sms = 1;
     const int grid = p.tiles < sms ? p.tiles : sms;
-    gemm_tf32x3_kernel<<<grid, GX_THREADS, GX_SMEM, st>>>(ops->ah, ops->al, ops->bh, ops->bl, p);
+    if (tma_epi)
+        gemm_tf32x3_kernel<true><<<grid, GX_THREADS, GX_SMEM_TMA, st>>>(ops->ah, ops->al, ops->bh, ops->bl, cmap->map, p);
+    else
+        gemm_tf32x3_kernel<false><<<grid, GX_THREADS, GX_SMEM, st>>>(ops->ah, ops->al, ops->bh, ops->bl, ops->ah, p);
     TQ_LAUNCH_CHECK("gemm_tf32x3_kernel");
     return 0;
 }

@@ -47,6 +47,12 @@ constexpr int HT_GI = 28, HT_GJ = 14, HT_MAX_GROUPS = 136;
 
 struct TileSched {
     int nbi, nbj, gdim, ngroups, num_chunks;
+    int round_ctas, items_per_cta;        // CTA c works on items (c / round_ctas) * round_ctas * items_per_cta + c % round_ctas
+                                          // + j * round_ctas, j < items_per_cta: inside a round the CTAs interleave over
+                                          // consecutive items exactly like a persistent grid would (same L2 locality), but a
+                                          // CTA retires after ~0.15 ms, so the block scheduler can hand its SM to a
+                                          // higher-priority stream (the dependent-kernel chains of linears whose Hessian is
+                                          // already complete) instead of holding every SM for the whole launch
     int tile_prefix[HT_MAX_GROUPS + 1];   // tiles in groups [0, g)
 
     __host__ __device__ static int tiles_in_col(int bj, int bi0, int bi1) {   // valid bi in [bi0, bi1): bi <= 2*bj + 1
@@ -122,11 +128,16 @@ hessian_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
 
     const long long total_items = sched.total_items();
+    const long long item0 = (long long)(blockIdx.x / sched.round_ctas) * sched.round_ctas * sched.items_per_cta +
+                            blockIdx.x % sched.round_ctas;
+    const int item_stride = sched.round_ctas, my_items = sched.items_per_cta;
 
     if (warp == 0 && lane == 0) {
         // ===== TMA producer =====
         int stage = 0, phase = 0;
-        for (long long it = blockIdx.x; it < total_items; it += gridDim.x) {
+        for (int ji = 0; ji < my_items; ++ji) {
+            const long long it = item0 + (long long)ji * item_stride;
+            if (it >= total_items) break;
             int chunk, bi, bj;
             sched.decode(it, chunk, bi, bj);
             const int t0 = chunk * kc;
@@ -148,7 +159,9 @@ hessian_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
         int stage = 0, phase = 0, n_item = 0;
-        for (long long it = blockIdx.x; it < total_items; it += gridDim.x, ++n_item) {
+        for (int ji = 0; ji < my_items; ++ji, ++n_item) {
+            const long long it = item0 + (long long)ji * item_stride;
+            if (it >= total_items) break;
             int chunk, bi, bj;
             sched.decode(it, chunk, bi, bj);
             const int t0 = chunk * kc;
@@ -180,7 +193,9 @@ hessian_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         const int row = q * 32 + lane;                   // row of the 128-row tile
         const bool leader = (warp == 4 && lane == 0);
         int n_item = 0, estage = 0;
-        for (long long it = blockIdx.x; it < total_items; it += gridDim.x, ++n_item) {
+        for (int ji = 0; ji < my_items; ++ji, ++n_item) {
+            const long long it = item0 + (long long)ji * item_stride;
+            if (it >= total_items) break;
             int chunk, bi, bj;
             sched.decode(it, chunk, bi, bj);
             const int acc = n_item & 1;
@@ -283,7 +298,10 @@ int hessian_accum_tcgen05(float* H, int64_t ldh, const void* X, int64_t Nt, int6
 
     // token chunk = one TMEM accumulation: small enough that the group's slab of X (chunk x <= 7168 cols x 2 B) plus the
     // group's H tiles stay L2-resident, capped at 2048 tokens (see below), and giving >= ~6 work items per SM
-    const int sms = sm_count();
+    // TQ_HESS_SPARE_SMS: SMs this persistent kernel leaves to the chains of other linears (inverse / sweep kernels on other
+    // streams) that run while the remaining Hessians of the layer are still being accumulated
+    static const int spare = []() { const char* e = getenv("TQ_HESS_SPARE_SMS"); return e ? atoi(e) : 0; }();
+    const int sms = (sm_count() - spare > 16) ? sm_count() - spare : sm_count();
     int64_t kc_l2 = (40ll << 20) / (2 * (m < 7168 ? m : 7168));
     kc_l2 = (kc_l2 / HT_BK) * HT_BK;
     if (kc_l2 < 256) kc_l2 = 256;
@@ -309,7 +327,13 @@ int hessian_accum_tcgen05(float* H, int64_t ldh, const void* X, int64_t Nt, int6
         TQ_CUDA(cudaFuncSetAttribute(hessian_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM));
         attr_set = true;
     }
-    const int grid = (int)((items < sms) ? items : sms);
+    // TQ_HESS_ITEMS_PER_CTA: work items (one <= 2048-token chunk of one 128 x 256 tile, ~9 us) a CTA processes before it
+    // retires; 0 = persistent (one CTA per SM for the whole launch)
+    static const int ipc_env = []() { const char* e = getenv("TQ_HESS_ITEMS_PER_CTA"); return e ? atoi(e) : 16; }();
+    sched.round_ctas = (int)((items < sms) ? items : sms);
+    const int64_t per_cta_persistent = ceil_div(items, sched.round_ctas);
+    sched.items_per_cta = (int)((ipc_env > 0 && ipc_env < per_cta_persistent) ? ipc_env : per_cta_persistent);
+    const int grid = (int)(ceil_div(items, (int64_t)sched.round_ctas * sched.items_per_cta) * sched.round_ctas);
     hessian_tc_kernel<<<grid, HT_THREADS, HT_SMEM, st>>>(map_x, map_h, (int)Nt, (int)kc, sched, idesc);
     TQ_LAUNCH_CHECK("hessian_tc_kernel");
     return 0;

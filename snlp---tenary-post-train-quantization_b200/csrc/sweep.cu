@@ -123,6 +123,9 @@ extern "C" int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const
     float* coef_hi = ws.coef;
     float* coef_lo = ws.coef + m * ldb;
     GemmOperands ops_full, ops_tail;
+    GemmC c_W;                  // W as the output matrix of the TMA epilogue (contiguous remaining columns only)
+    c_W.valid = false;
+    if (tc_feedback && order == TQ_ORDER_SEQUENTIAL && (rc = gemm_cmap_encode(&c_W, W, n, m, ldw))) return rc;
     const int64_t tail = m % block;
     if (tc_feedback) {
         if (m > block && (rc = gemm_operands_encode(&ops_full, ws.E, ws.E_lo, ldb, n, coef_hi, coef_lo, ldb, m, block))) return rc;
@@ -201,6 +204,8 @@ extern "C" int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const
                     rs ^= 1;
                     rs_parts = 2 * ceil_div(rem, 128);
                     have_stats = true;
+                } else if (c_W.valid && rem_idx == nullptr) {
+                    rc = launch_gemm_tf32x3_at(GX_FEEDBACK, &c_W, 0, done + b, n, rem, ops, 0, 0, st);
                 } else {
                     rc = launch_gemm_tf32x3_ops(GX_FEEDBACK, W, ldw, n, rem, ops, rem_idx, done + b, st);
                 }

@@ -53,6 +53,11 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32
                  ::"l"(map), "r"(src), "r"(c0), "r"(c1)
                  : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -123,6 +128,12 @@ struct GemmOperands {
     CUtensorMap ah, al, bh, bl;     // TMA descriptors of the four operand arrays
     int64_t K;
 };
+struct GemmC {                      // output matrix of the TMA epilogue (gemm_cmap_encode)
+    CUtensorMap map;
+    float* base;
+    int64_t ld;
+    bool valid;
+};
 enum GxMode {
     GX_FEEDBACK = 0,      // all tiles; C[r, colmap(j)] -= acc
     GX_SUB_LOWER = 1,     // tiles bi >= bj; C[r, c] -= acc for c <= r  (potrf trailing update)
@@ -135,6 +146,9 @@ int launch_gemm_tf32x3_rows(int mode, float* C, int64_t ldc, int64_t M, int64_t 
                             int64_t b_row0, const int32_t* col_idx, int64_t col0, cudaStream_t st);
 int launch_gemm_tf32x3_ops(int mode, float* C, int64_t ldc, int64_t M, int64_t N, const GemmOperands* ops,
                            const int32_t* col_idx, int64_t col0, cudaStream_t st);
+int gemm_cmap_encode(GemmC* c, float* base, int64_t rows, int64_t cols, int64_t ld);
+int launch_gemm_tf32x3_at(int mode, const GemmC* cmap, int64_t c_row0, int64_t c_col0, int64_t M, int64_t N,
+                          const GemmOperands* ops, int64_t a_row0, int64_t b_row0, cudaStream_t st);
 int launch_gemm_tf32x3(int mode, float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, const float* Ah, const float* Al,
                        int64_t lda, const float* Bh, const float* Bl, int64_t ldb, const int32_t* col_idx, int64_t col0,
                        cudaStream_t st);

@@ -7,6 +7,7 @@ traffic of the next input overlaps Hessian + sweep of the current one.  This is 
 """
 
 import collections
+import os
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
 import torch
@@ -36,10 +37,21 @@ class LayerDriver:
     and overlap on the GPU; the Hessian GEMMs, which saturate the device, stay on the caller's stream."""
 
     def __init__(self, device, block_size: int = 128, percdamp: float = 0.01, num_streams: int = 4,
-                 share_inputs: bool = False):
+                 share_inputs: bool = False, eager_chains: Optional[bool] = None):
         self.device = torch.device(device)
         self.block_size, self.percdamp, self.share_inputs = block_size, percdamp, share_inputs
-        self.streams = [torch.cuda.Stream(self.device) for _ in range(max(1, num_streams))]
+        num_streams = int(os.environ.get("TQ_CHAIN_STREAMS", num_streams))
+        # the stream that gets the longest chain outranks the others: its small dependent kernels are placed first
+        # whenever SMs free up (TQ_CHAIN_PRIORITY=0 gives every stream the default priority)
+        # CUDA priorities: numerically lower = served first; the caller's stream (where the Hessian kernels run) is 0, the
+        # lowest.  Chain streams sit above it -- their short dependent kernels take SMs as Hessian CTAs retire -- and the
+        # first stream, which gets the longest chain, sits above the other chains.
+        prio = os.environ.get("TQ_CHAIN_PRIORITY", "1") != "0"
+        self.streams = [torch.cuda.Stream(self.device, priority=((-3 if i == 0 else -1) if prio else 0))
+                        for i in range(max(1, num_streams))]
+        # eager: a linear's chain starts as soon as ITS Hessian is complete and overlaps the Hessians still running
+        # (widest input first, so the longest chain starts first); otherwise all chains wait for all Hessians
+        self.eager = (os.environ.get("TQ_EAGER_CHAINS", "1") != "0") if eager_chains is None else bool(eager_chains)
 
     def quantize(self, linears, use_ssr: bool = True, aga: str = "hessian", max_iter: int = 100, hess_timing=None,
                  order: Optional[str] = None):
@@ -48,10 +60,17 @@ class LayerDriver:
         None follows use_ssr).  Returns [GPTQ] in order, quantized."""
         main = torch.cuda.current_stream(self.device)
         shared = {}
-        gs = []
-        for name, W, X in linears:
+        gs = [None] * len(linears)
+        ready = [None] * len(linears)
+        # Hessian order (TQ_HESS_ORDER): 'short-first' (default) accumulates the Hessians of the short chains first, so
+        # those chains run underneath the remaining -- SM-filling -- Hessian kernels and the longest chain, which starts
+        # last, has the GPU almost to itself; 'long-first' starts the longest chain as early as possible instead
+        sign = 1 if os.environ.get("TQ_HESS_ORDER", "short-first") == "short-first" else -1
+        seq = sorted(range(len(linears)), key=lambda i: (sign * chain_cost(*linears[i][1].shape), i))
+        for i in seq:
+            name, W, X = linears[i]
             st = shared.get(id(X)) if self.share_inputs else None
-            g = GPTQ(LinearView(W), self.block_size, self.percdamp, hessian=st)
+            g = GPTQ(LinearView(W), self.block_size, self.percdamp, hessian=st[0] if st else None)
             if st is None:
                 if hess_timing is not None:
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -60,10 +79,19 @@ class LayerDriver:
                 if hess_timing is not None:
                     e1.record()
                     hess_timing.append((e0, e1, X.numel() // X.shape[-1], W.shape[1]))
+                ev = torch.cuda.Event()
+                ev.record(main)
                 if self.share_inputs:
-                    shared[id(X)] = g.state
-            gs.append(g)
-        return self.run_chains(gs, use_ssr=use_ssr, aga=aga, max_iter=max_iter, order=order)
+                    shared[id(X)] = (g.state, ev)
+            else:
+                ev = st[1]
+            gs[i], ready[i] = g, ev
+        if not self.eager:
+            last = torch.cuda.Event()
+            last.record(main)
+            ready = [last] * len(linears)
+        return self.finish_chains(gs, self.enqueue_chains(gs, use_ssr=use_ssr, aga=aga, max_iter=max_iter, order=order,
+                                                          ready=ready))
 
     def run_chains(self, gs, use_ssr: bool = True, aga: str = "hessian", max_iter: int = 100, order: Optional[str] = None):
         """Prologue + sweep of every GPTQ in ``gs`` (Hessians already accumulated on the current stream), longest
@@ -71,15 +99,23 @@ class LayerDriver:
         return self.finish_chains(gs, self.enqueue_chains(gs, use_ssr=use_ssr, aga=aga, max_iter=max_iter, order=order))
 
     def enqueue_chains(self, gs, use_ssr: bool = True, aga: str = "hessian", max_iter: int = 100,
-                       order: Optional[str] = None):
-        """Asynchronous half of run_chains(): returns the order to hand to finish_chains()."""
+                       order: Optional[str] = None, ready=None):
+        """Asynchronous half of run_chains(): returns the order to hand to finish_chains().  ``ready``: per GPTQ, the
+        event after which its Hessian is complete (default: everything enqueued on the current stream so far).
+        Chains go longest first onto the least-loaded stream (by estimated duration), so the longest chain has the
+        first -- high-priority -- stream to itself for as long as the others have work elsewhere."""
         main = torch.cuda.current_stream(self.device)
-        ready = torch.cuda.Event()
-        ready.record(main)
-        seq = sorted(range(len(gs)), key=lambda i: -chain_cost(gs[i].rows, gs[i].columns))
-        for slot, i in enumerate(seq):
-            s = self.streams[slot % len(self.streams)]
-            s.wait_event(ready)
+        if ready is None:
+            ev = torch.cuda.Event()
+            ev.record(main)
+            ready = [ev] * len(gs)
+        seq = sorted(range(len(gs)), key=lambda i: (-chain_cost(gs[i].rows, gs[i].columns), i))
+        load = [0.0] * len(self.streams)
+        for i in seq:
+            slot = min(range(len(self.streams)), key=lambda k: (load[k], k))
+            load[slot] += chain_cost(gs[i].rows, gs[i].columns)
+            s = self.streams[slot]
+            s.wait_event(ready[i])
             with torch.cuda.stream(s):
                 gs[i].enqueue(use_ssr=use_ssr, aga=aga, max_iter=max_iter, order=order)
         return seq

@@ -109,11 +109,14 @@ def clean_prefix_mask(Ta, Tb, perm, block_size):
     return np.logical_and.accumulate(pairs, axis=1)
 
 
-def adjudicate(got, ref, margin=None, block_size=128):
-    """SURVEY 8c adjudication of one layer: got / ref are dicts with alpha, mu, T, perm; ``margin`` (optional, (n, m)) is
-    | |Z| - 0.5 | of the reference's final rounding per code (original positions).  Returns a JSON-able report:
-    code agreement, block membership, scale errors on clean (row, block) pairs, and for every row that diverges the
-    smallest margin among its disagreeing codes in the FIRST block where it diverges (tie evidence)."""
+def adjudicate(got, ref, aids=None, block_size=128):
+    """SURVEY 8c adjudication of one layer: got / ref are dicts with alpha, mu, T, perm; ``aids`` (optional) is the fifth
+    output of oracle.torch_port.quantize_layer(return_margin=True), as numpy arrays: 'final' (n, m) = | |Z| - 0.5 | of
+    the reference's final rounding per code, 'trajectory' (n, nb) = the smallest margin the row met at any rounding of
+    the block, 'topk_gap' (nb,) = similarity gap at each SSR top-k boundary.  Returns a JSON-able report: code
+    agreement, block membership, scale errors on clean (row, block) pairs, and -- the tie evidence -- for every row that
+    diverges, the margins in the FIRST block where it diverges; for SSR, the top-k gap and the number of swapped
+    columns at the first block whose membership differs."""
     Tg, Tr = np.asarray(got["T"]).astype(np.int8), np.asarray(ref["T"]).astype(np.int8)
     pg, pr = np.asarray(got["perm"]), np.asarray(ref["perm"])
     n, m = Tr.shape
@@ -129,9 +132,13 @@ def adjudicate(got, ref, margin=None, block_size=128):
             break
         lead += 1
     rep["leading_blocks_same_membership"] = lead
+    if lead < nb:
+        a, b = set(pg[lead * block_size:(lead + 1) * block_size].tolist()), set(pr[lead * block_size:(lead + 1) * block_size].tolist())
+        rep["first_differing_block"] = {"index": lead, "columns_swapped": len(a - b)}
+        if aids is not None and aids.get("topk_gap") is not None:
+            rep["first_differing_block"]["reference_topk_gap"] = float(aids["topk_gap"][lead])
     if lead == 0:
         return rep
-    cols_ok = lead * block_size
     pairs = block_pairs_agree(Tg, Tr, pr, block_size)[:, :lead]
     clean = np.logical_and.accumulate(pairs, axis=1)
     a_ref = np.asarray(ref["alpha"], dtype=np.float64)[:, :lead]
@@ -146,17 +153,25 @@ def adjudicate(got, ref, margin=None, block_size=128):
     rep["alpha_rel_err_max"] = scale_rel_err(np.asarray(got["alpha"])[:, :lead], a_ref, mask)
     rep["mu_err_rel_alpha_max"] = scale_rel_err(np.asarray(got["mu"])[:, :lead], np.asarray(ref["mu"])[:, :lead], mask,
                                                 floor=np.abs(a_ref))
-    if margin is not None and rep["rows_diverged"]:
-        margin = np.asarray(margin, dtype=np.float64)
+    if aids is not None and rep["rows_diverged"]:
+        final = np.asarray(aids["final"], dtype=np.float64)
+        traj = np.asarray(aids["trajectory"], dtype=np.float64)
         first_bad = np.argmin(clean, axis=1)                    # first block where the row is no longer clean
-        mins = []
+        fin, trj = [], []
         for r in np.nonzero(~clean[:, -1])[0]:
             cols = pr[first_bad[r] * block_size:(first_bad[r] + 1) * block_size]
             bad = cols[Tg[r, cols] != Tr[r, cols]]
             if bad.size:
-                mins.append(float(margin[r, bad].min()))
-        if mins:
-            mins = np.sort(np.asarray(mins))
-            rep["tie_margin_first_divergence"] = {"rows": int(mins.size), "median": float(np.median(mins)),
-                                                  "p90": float(mins[int(0.9 * (mins.size - 1))]), "max": float(mins[-1])}
+                fin.append(float(final[r, bad].min()))
+                trj.append(float(traj[r, first_bad[r]]))
+
+        def stats(v):
+            v = np.sort(np.asarray(v))
+            return {"rows": int(v.size), "median": float(np.median(v)), "p90": float(v[int(0.9 * (v.size - 1))]),
+                    "max": float(v[-1])}
+        if fin:
+            rep["tie_margin_first_divergence"] = stats(trj)             # smallest margin on the ITF trajectory
+            rep["tie_margin_final_rounding"] = stats(fin)               # margin of the flipped codes at the last rounding
+            # what a row that did NOT diverge typically meets: the yardstick the margins above are read against
+            rep["trajectory_margin_all_rows_median"] = float(np.median(traj[:, :lead]))
     return rep

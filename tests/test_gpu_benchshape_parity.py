@@ -8,7 +8,8 @@ and the product differ: accumulation order and the fp32-emulating tensor-core GE
 Tolerances are north_star's: codes >= 99.9 %, alpha / mu within 1e-4 relative on (row, block) pairs no earlier flip has
 touched, reconstruction error within 1e-3 relative.  Every disagreement is adjudicated: the margin
 | |Z| - 0.5 | of the reference's rounding at the first block where a row diverges -- a threshold tie -- is reported and
-bounded.  With SSR one swapped top-k boundary legitimately de-correlates everything after it (the reference does not
+bounded (the smallest margin on the row's ITF trajectory: a tie several iterations before the last can tip a row into a
+different fixed point).  With SSR one swapped top-k boundary legitimately de-correlates everything after it (the reference does not
 reproduce itself there), so SSR cases assert block by block on the leading blocks whose membership
 agrees, always the first block, and the reconstruction error; the report says how many blocks agreed.
 
@@ -67,6 +68,10 @@ def _dequant(alpha, mu, T, perm, block=128):
     return Wq
 
 
+def _np_aids(aids):
+    return {k: (v.numpy() if torch.is_tensor(v) else v) for k, v in aids.items()}
+
+
 def _save(tag, rep):
     _report[tag] = rep
     out = os.path.join(ROOT, "gpurun_out")
@@ -93,10 +98,10 @@ def test_bench_shape_layer_vs_oracle(n, m, order):
     assert q.info == 0
     Wq = q.get_quantized_weight()
     Wc = W.cpu()
-    ra, ru, rT, rp, margin = torch_port.quantize_layer(Wc, H_ref, NT, 128, 0.01, use_ssr=use_ssr, return_margin=True)
+    ra, ru, rT, rp, aids = torch_port.quantize_layer(Wc, H_ref, NT, 128, 0.01, use_ssr=use_ssr, return_margin=True)
     got = dict(alpha=alpha.cpu().numpy(), mu=mu.cpu().numpy(), T=T.cpu().numpy(), perm=perm.cpu().numpy())
     ref = dict(alpha=ra.numpy(), mu=ru.numpy(), T=rT.numpy(), perm=rp.numpy())
-    rep = parity.adjudicate(got, ref, margin.numpy())
+    rep = parity.adjudicate(got, ref, _np_aids(aids))
     e_got = _recon(Wc, Wq.cpu(), H_ref)
     e_ref = _recon(Wc, _dequant(ra, ru, rT, rp), H_ref)
     rep.update(recon_got=e_got, recon_ref=e_ref, recon_rel_diff=abs(e_got - e_ref) / e_ref, order=order, tokens=NT)
@@ -120,8 +125,10 @@ def test_bench_shape_layer_vs_oracle(n, m, order):
     assert rep["mu_err_rel_alpha_max"] <= parity.SCALE_RTOL, rep
     tie = rep.get("tie_margin_first_divergence")
     if tie is not None:
-        # disagreements start at threshold ties: a code flips only where |Z| sits within fp32 noise of 0.5
-        assert tie["median"] <= 1e-3, rep
+        # disagreements start at threshold ties: a row leaves the reference's trajectory only where some rounding on its
+        # ITF path had |Z| within fp32 noise of 0.5 (a row that does not diverge typically stays ~1e-3 away, recorded in
+        # the report as trajectory_margin_all_rows_median)
+        assert tie["median"] <= 5e-5, rep
 
 
 def test_oracle_fp32_vs_fp64_floor_4096():
@@ -134,9 +141,9 @@ def test_oracle_fp32_vs_fp64_floor_4096():
     a32, u32, T32, p32 = torch_port.quantize_layer(Wc, H_ref, NT, 128, 0.01, use_ssr=False)
     Xd = X.double().cpu()
     H64 = Xd.T @ Xd
-    a64, u64, T64, p64, margin = torch_port.quantize_layer(Wc.double(), H64, NT, 128, 0.01, use_ssr=False, return_margin=True)
+    a64, u64, T64, p64, aids = torch_port.quantize_layer(Wc.double(), H64, NT, 128, 0.01, use_ssr=False, return_margin=True)
     r64 = dict(alpha=a64.numpy(), mu=u64.numpy(), T=T64.numpy(), perm=p64.numpy())
-    floor = parity.adjudicate(dict(alpha=a32.numpy(), mu=u32.numpy(), T=T32.numpy(), perm=p32.numpy()), r64, margin.numpy())
+    floor = parity.adjudicate(dict(alpha=a32.numpy(), mu=u32.numpy(), T=T32.numpy(), perm=p32.numpy()), r64, _np_aids(aids))
     _save("floor_4096x4096_sequential_ref32_vs_ref64", floor)
     got = _report.get("4096x4096_sequential")
     if got is not None:
