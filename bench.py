@@ -102,6 +102,8 @@ def find_reference_dir():
     """The unmodified reference, if this machine has it: $TQ_REFERENCE_DIR, baseline/_ref, /root/reference.
     It is a flat directory of Python scripts, not an installable package, and does not exist on the GPU box; there the
     oracle's port (oracle/torch_port.py, pinned to the reference's outputs by tests/test_oracle_golden.py) stands in."""
+    if os.environ.get("TQ_BENCH_FORCE_PORT"):            # A/B of the port against the reference on the same cores
+        return None
     for d in (os.environ.get("TQ_REFERENCE_DIR"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
         if d and os.path.isfile(os.path.join(d, "gptq.py")) and os.path.isfile(os.path.join(d, "quantizer.py")):
             return d
@@ -449,6 +451,94 @@ def sharded_parity_leg(torch, dist, tq100, args, ctx, order, lins, w_last, acts,
                                                       sharded_layer.owners([(a_, b_) for _, a_, b_, _ in lins])[i] < 0)}
     rep["ok"] = all(v["min_code_agreement_over_ranks"] >= 0.999 for v in rep["linears"].values())
     return rep
+
+
+# ------------------------------------------------------------------------------------ configs[4]: single-layer sweep
+def layer_sweep_line(args):
+    """BASELINE configs[4]: single linears 4096x4096 ... 8192x28672, each stage timed alone (best of 3, CUDA events) and
+    put against its roofline: Hessian vs the measured bf16 peak (useful SYRK flops), damped inverse (m^3 flops), the
+    column sweep in sequential and SSR order vs the measured HBM copy peak on the algorithmic bytes of SURVEY 8d
+    (read-modify-write of the remaining columns per block + the block's own reads and writes)."""
+    import torch
+    import tq100
+    from tq100.pipeline import LinearView
+    dev = torch.device("cuda:0")
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tf_peak, hbm_peak = peaks.get("bf16_tflops", 1590.0), peaks.get("hbm_gbs", 6650.0)
+    nt = SAMPLES * SEQ
+    shapes = [(4096, 4096), (11008, 4096), (4096, 11008), (5120, 5120), (13824, 5120), (5120, 13824),
+              (8192, 8192), (28672, 8192), (8192, 28672)]
+    if args.layers:
+        shapes = shapes[:args.layers]
+
+    def best_of(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return min(ts)
+
+    rows = []
+    launches0 = tq100._lib.launch_count()
+    for n, m in shapes:
+        g = torch.Generator(device=dev).manual_seed(n + m)
+        X = torch.empty((nt, m), device=dev, dtype=torch.float16)
+        for lo in range(0, nt, 32768):
+            X[lo:lo + 32768] = torch.randn((min(32768, nt - lo), m), device=dev, generator=g).to(torch.float16)
+        W = torch.randn((n, m), device=dev, generator=g) * 0.02
+        q = tq100.GPTQ(LinearView(W))
+        st = q.state
+
+        def hess():
+            st.H.zero_()
+            st.nsamples = 0
+            st.add_batch(X)
+        t_h = best_of(hess, max(1, args.steps))
+
+        def inv():
+            st._cache.clear()
+            st.damped_inverse(0.01)
+        t_inv = best_of(inv, max(1, args.steps))
+        nb = (m + 127) // 128
+        rmw = sum(8 * n * (m - 128 * (k + 1)) for k in range(nb - 1))              # feedback RMW of W[:, rem] per block
+        blk = n * m * (4 + 1 + 8)                                                  # block read, codes, E (hi, lo)
+        rec = {"n": n, "m": m, "tokens": nt, "hessian_ms": t_h,
+               "hessian_tflops_useful": hessian_useful_flops(nt, m) / t_h / 1e9,
+               "hessian_frac_of_bf16_burst_peak": hessian_useful_flops(nt, m) / t_h / 1e9 / tf_peak,
+               "inverse_ms": t_inv, "inverse_tflops_fp32_equiv": m ** 3 / t_inv / 1e9}
+        for key, kw, extra in (("sweep_seq", dict(use_ssr=False), 0), ("sweep_ssr", dict(use_ssr=True), 2 * 4 * n * m)):
+            t = best_of(lambda: q.quantize(**kw), max(1, args.steps)) - t_inv * 0.0
+            # quantize() reuses the cached inverse: the time is the sweep alone.  SSR adds the first block's two
+            # statistics passes over W; later blocks take their statistics from the feedback epilogue (no extra bytes)
+            gb = (rmw + blk + extra) / 1e9
+            rec[key + "_ms"] = t
+            rec[key + "_algorithmic_gb"] = gb
+            rec[key + "_gbs"] = gb / t * 1e3
+            rec[key + "_frac_of_hbm_peak"] = gb / t * 1e3 / hbm_peak
+        rows.append(rec)
+        print(json.dumps(rec), file=sys.stderr, flush=True)
+        del X, W, q, st
+        torch.cuda.empty_cache()
+    line = {"metric": METRIC["layer-sweep"], "value": sum(r["hessian_ms"] + r["inverse_ms"] + r["sweep_ssr_ms"] for r in rows) / 1e3,
+            "unit": "s", "n_gpus": 1, "steps": args.steps, "warmup": 1, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "single-layer sweep, one linear at a time: Hessian over 128x2048 fp16 tokens, damped inverse, "
+                                   "column sweep (sequential and SSR), block 128", "baseline_config": "configs[4]",
+                       "cache": "each stage's inputs exceed L2 except the 4096-wide inverses; no explicit flush"},
+            "peaks": {"bf16_tflops_burst": tf_peak, "hbm_gbs": hbm_peak, "source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+            "gpu_launches": int(tq100._lib.launch_count() - launches0), "rows": rows,
+            "value_note": "sum over the shapes of Hessian + inverse + SSR sweep, each timed alone"}
+    print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------ N2 leg

@@ -15,8 +15,8 @@ for _ in range(2):
     G.finalize_and_invert(H, 2048)
 t = buf.cpu().numpy()
 t = t[t > 0]
-names = ["load"] + sum([[f"factor{d}", f"solve{d}", f"update{d}"] for d in range(4)], []) + ["inv_diag", "lev1", "lev2", "lev3", "store"]
+names = ["load"] + sum([[f"factor+invert{d}", f"rows_below+Vrow{d}", f"update{d}"] for d in range(4)], []) + ["store"]
 d = np.diff(t)
 for nme, c in zip(names, d):
-    print(f"{nme:10s} {c:8d} cycles")
+    print(f"{nme:18s} {c:8d} cycles")
 print("total", t[-1] - t[0], "cycles")

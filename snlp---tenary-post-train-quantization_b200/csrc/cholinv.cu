@@ -29,46 +29,85 @@ constexpr int CB = 128;            // panel width
 constexpr int CB_LD = CB + 1;      // shared-memory row stride
 constexpr int DIAG_THREADS = 512;
 
-// One CTA factors a 128x128 diagonal block and inverts its Cholesky factor, all in shared memory, in four
-// 32-column steps:  warp 0 factors the 32x32 diagonal sub-block with its rows in registers (pivots and
-// multipliers travel by shuffle), the rows below are solved against it one thread per row, the trailing
-// sub-blocks take the rank-32 update.  The inverse is built the same way: four warps invert the 32x32
-// diagonal sub-blocks, then the off-diagonal sub-blocks follow level by level as 32x32 products.
 constexpr int SB = 32;                 // sub-block width
 constexpr int NSB = CB / SB;           // 4
 
-// One warp factors a 32x32 diagonal sub-block; lane i holds row i in registers.  Each column step publishes the
-// freshly scaled column through a 32-float shared buffer that every lane reads back as eight 128-bit broadcast
-// loads (independent, so they pipeline -- a shuffle per multiplier would stall the in-order issue 31 times).
-__device__ __forceinline__ void diag_factor_32(float* S, float* colbuf, int o, int nb, int k0, int* info, int lane) {
+// ---- diagonal-block kernel, second form --------------------------------------------------------------------------
+// One CTA factors a 128x128 diagonal block A = L L' and inverts L, in four 32-column steps.  The only serial part is the
+// 32x32 diagonal sub-block: warp 0 factors it with its rows in registers and inverts the factor right away (lane = column
+// of the inverse).  Everything else is a small shared-memory matrix product spread over all warps:
+//   rows below       L21 = A21 V11'                      (V11 = L11^-1: no substitution chain)
+//   trailing update  A22 -= L21 L21'
+//   inverse, row d   V[d, j<d] = -V_dd (sum_k L[d,k] V[k,j]); the inner sum runs on warps 1.. WHILE warp 0 factors
+//                    block d (it needs only rows of L and V that are already final)
+constexpr int DG_P_LD = 3 * SB + 1;      // scratch P: 32 rows x (up to 96 columns)
+
+// 1 / sqrt(p): hardware approximation + one Newton step (relative error ~1 ulp)
+__device__ __forceinline__ float fast_rsqrt(float p) {
+    float r = rsqrtf(p);
+    return r * fmaf(-0.5f * p, r * r, 1.5f);
+}
+
+// warp 0: S[o:o+32, o:o+32] -> L_dd (in place, upper part zeroed) and V[o:o+32, o:o+32] = L_dd^-1.
+// This code runs once per launch on a single warp, so it has to be SHORT as well as register-resident: fully unrolled over
+// the 32 columns (several thousand straight-line instructions) it is bound by instruction fetch (measured 38k cycles per
+// sub-block), and with the block left in shared memory by load latency (47k).  Hence the ROTATING register file: lane i
+// keeps row i in a[0..31] and after every column the row is shifted left by one, so the current column is always a[0] and
+// the loop body does not depend on the column index -- one rolled loop of ~60 instructions.  The multipliers of the other
+// rows travel through a 32-float buffer indexed by (row - column), read back as eight 128-bit broadcast loads.
+__device__ __forceinline__ void diag_factor_invert_32(float* S, float* V, float* colbuf, float* rdiag, int o, int nb, int k0,
+                                                      int* info, int lane) {
     float a[SB];
+    float* myrow = S + (o + lane) * CB_LD + o;
 #pragma unroll
-    for (int c = 0; c < SB; ++c) a[c] = S[(o + lane) * CB_LD + o + c];
-#pragma unroll
+    for (int c = 0; c < SB; ++c) a[c] = myrow[c];
+#pragma unroll 1
     for (int j = 0; j < SB; ++j) {
-        float pj = __shfl_sync(0xffffffffu, a[j], j);
+        const int rel = lane - j;                            // row index relative to the pivot row
+        float pj = __shfl_sync(0xffffffffu, a[0], j);
         if (!(pj > 0.f)) {                                   // also catches NaN
             if (lane == 0 && o + j < nb) atomicCAS(info, 0, k0 + o + j + 1);
             pj = 1.f;                                        // keep going so nothing downstream divides by zero
         }
-        const float rinv = __frsqrt_rn(pj);
-        const float l = (lane == j) ? __fmul_rn(pj, rinv) : __fmul_rn(a[j], rinv);
-        a[j] = l;
-        colbuf[lane] = l;
+        const float rinv = fast_rsqrt(pj);
+        const float l = (rel == 0) ? pj * rinv : ((rel > 0) ? a[0] * rinv : 0.f);
+        myrow[j] = l;                                        // L[i][j]; zero above the diagonal
+        if (rel == 0) rdiag[j] = rinv;
+        float* cb = colbuf + (j & 1) * SB;                   // double-buffered: one warp barrier per column
+        cb[rel & (SB - 1)] = l;
         __syncwarp();
-        float lc[SB];
+        float lc[SB];                                        // lc[t] = multiplier of row j + t
 #pragma unroll
         for (int v = 0; v < SB / 4; ++v) {
-            const float4 t = *reinterpret_cast<const float4*>(colbuf + 4 * v);
+            const float4 t = *reinterpret_cast<const float4*>(cb + 4 * v);
             lc[4 * v] = t.x; lc[4 * v + 1] = t.y; lc[4 * v + 2] = t.z; lc[4 * v + 3] = t.w;
         }
+        // a[t] holds column j + t of this row: update columns j + t <= row (t <= rel) and shift left
 #pragma unroll
-        for (int c = j + 1; c < SB; ++c)
-            if (lane >= c) a[c] = fmaf(-l, lc[c], a[c]);
-        __syncwarp();
+        for (int t = 1; t < SB; ++t) a[t - 1] = (t <= rel) ? fmaf(-l, lc[t], a[t]) : a[t];
+        a[SB - 1] = 0.f;
     }
+    __syncwarp();
+    // inverse: lane q owns column q of V_dd.  acc[t] accumulates row i + t of  delta - L x ; when x_i = acc[0] / L[i][i] is
+    // known every later row takes its contribution (column i of L: warp-uniform addresses, broadcast loads) and the
+    // accumulators shift -- again a column-independent loop body
+    float acc[SB];
 #pragma unroll
-    for (int c = 0; c < SB; ++c) S[(o + lane) * CB_LD + o + c] = (c <= lane) ? a[c] : 0.f;
+    for (int t = 0; t < SB; ++t) acc[t] = (t == lane) ? 1.f : 0.f;
+    float* vcol = V + o * CB_LD + o + lane;
+#pragma unroll 1
+    for (int i = 0; i < SB; ++i) {
+        const float x = acc[0] * rdiag[i];                   // 0 for i < q: nothing has reached the accumulator yet
+        vcol[i * CB_LD] = x;
+        const float* lcol = S + (o + i) * CB_LD + o + i;     // L[i + t][i] at lcol[t * CB_LD] (zero rows past the block are
+                                                             // never read: t <= 31 - i is enforced by the clamp below)
+#pragma unroll
+        for (int t = 1; t < SB; ++t) {
+            const int tt = (i + t < SB) ? t : 0;             // clamp: rows past the sub-block contribute nothing useful
+            acc[t - 1] = fmaf(-lcol[tt * CB_LD], x, acc[t]);
+        }
+        acc[SB - 1] = 0.f;
+    }
 }
 
 __global__ void __launch_bounds__(DIAG_THREADS)
@@ -80,12 +119,12 @@ chol_diag_kernel(float* __restrict__ A, int64_t ld, int m, int k0, float* __rest
     TQ_PROF();
     float* S = sh;                       // [CB][CB_LD]  A_kk -> L_kk
     float* V = sh + CB * CB_LD;          // [CB][CB_LD]  L_kk^-1
-    float* Tm = sh + 2 * CB * CB_LD;     // [3][SB][SB+1] scratch for the off-diagonal inverse blocks
-    __shared__ __align__(16) float colbuf[SB];
+    float* P = sh + 2 * CB * CB_LD;      // [SB][DG_P_LD] partial products of the inverse's current block row
+    __shared__ float rdiag[SB];
+    __shared__ __align__(16) float colbuf[2 * SB];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nb = min(CB, m - k0);
-    // tid -> (row = tid / 4 + 128 * ..., 32 consecutive columns): each thread fetches its 32 values with eight
-    // independent 128-bit loads when the block is interior and aligned, else element-wise
+    // tid -> (row = tid / 4, 32 consecutive columns): eight independent 128-bit loads when the block is interior and aligned
     {
         const int i = tid >> 2, j0 = (tid & 3) * 32;
         const bool fast = (nb == CB) && ((ld & 3) == 0) && ((k0 & 3) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
@@ -114,92 +153,108 @@ chol_diag_kernel(float* __restrict__ A, int64_t ld, int m, int k0, float* __rest
     __syncthreads();
     TQ_PROF();
 
-    // ---- L = chol(S), right-looking over 32-column steps
     for (int d = 0; d < NSB; ++d) {
         const int o = d * SB;
-        if (warp == 0) diag_factor_32(S, colbuf, o, nb, k0, info, lane);
-        __syncthreads();
-        TQ_PROF();
         const int below = CB - o - SB;                           // rows under the diagonal sub-block
-        if (tid < below) {                                       // x L_dd' = a : one row per thread
-            float* row = S + (o + SB + tid) * CB_LD + o;
-            float x[SB];
+        if (warp == 0) {
+            diag_factor_invert_32(S, V, colbuf, rdiag, o, nb, k0, info, lane);
+        } else if (d > 0) {
+            // P[i][c] = sum_{k<o} L[o+i][k] V[k][c]  for c < o (V[k][c] = 0 for k < c).  Thread (i, g) owns the eight columns
+            // g + q * (o / 8): neighbouring threads read neighbouring columns of the same row of V (no bank conflicts), and
+            // every thread walks the same k (warp-uniform trip count)
+            const int t = tid - 32;
+            if (t < 4 * o) {
+                const int ng = o >> 3, i = t / ng, g = t - i * ng;
+                float acc[8];
 #pragma unroll
-            for (int j = 0; j < SB; ++j) {
-                float s = row[j];
+                for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+                const float* lrow = S + (o + i) * CB_LD;
+#pragma unroll 2
+                for (int k = 0; k < o; ++k) {
+                    const float l = lrow[k];
+                    const float* vrow = V + k * CB_LD + g;
 #pragma unroll
-                for (int k = 0; k < j; ++k) s = fmaf(-x[k], S[(o + j) * CB_LD + o + k], s);
-                x[j] = __fdiv_rn(s, S[(o + j) * CB_LD + o + j]);
+                    for (int q = 0; q < 8; ++q) acc[q] = fmaf(l, vrow[q * ng], acc[q]);
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) P[i * DG_P_LD + g + q * ng] = acc[q];
             }
-#pragma unroll
-            for (int j = 0; j < SB; ++j) row[j] = x[j];
         }
         __syncthreads();
         TQ_PROF();
-        if (below > 0) {                                         // trailing -= P P', 4 threads per row
-            const int r = o + SB + (tid >> 2);
-            if (r < CB) {
-                float pr[SB];
+        // L21 = A21 V_dd' : row r = o + 32 + tid / 4, eight columns per thread; the four threads of a row share a warp
+        {
+            const int rr = tid >> 2, j0 = (tid & 3) * 8;
+            float acc[8];
 #pragma unroll
-                for (int k = 0; k < SB; ++k) pr[k] = S[r * CB_LD + o + k];
-                for (int c = o + SB + (tid & 3); c <= r; c += 4) {
-                    float s = 0.f;
+            for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+            float* arow = S + (o + SB + rr) * CB_LD + o;
+            if (rr < below) {
+                for (int k = 0; k < j0 + 8; ++k) {               // V_dd[j][k] = 0 for k > j
+                    const float a = arow[k];
 #pragma unroll
-                    for (int k = 0; k < SB; ++k) s = fmaf(pr[k], S[c * CB_LD + o + k], s);
-                    S[r * CB_LD + c] -= s;
+                    for (int q = 0; q < 8; ++q) acc[q] = fmaf(a, V[(o + j0 + q) * CB_LD + o + k], acc[q]);
                 }
             }
+            __syncwarp();
+            if (rr < below) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) arow[j0 + q] = acc[q];
+            }
+        }
+        // inverse, block row d:  V[o+i][c] = -sum_{k<=i} V_dd[i][k] P[k][c]   (same thread -> column mapping as P)
+        if (d > 0 && tid < 4 * o) {
+            const int ng = o >> 3, i = tid / ng, g = tid - i * ng;
+            float acc[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+            const float* vdd = V + (o + i) * CB_LD + o;
+#pragma unroll 2
+            for (int k = 0; k < SB; ++k) {                       // V_dd[i][k] = 0 for k > i
+                const float v = vdd[k];
+                const float* prow = P + k * DG_P_LD + g;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] = fmaf(v, prow[q * ng], acc[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) V[(o + i) * CB_LD + g + q * ng] = -acc[q];
         }
         __syncthreads();
         TQ_PROF();
-    }
-
-    // ---- V = L^-1: diagonal sub-blocks, one warp each, lane = column of the inverse
-    if (warp < NSB) {
-        const int o = warp * SB;
-        float x[SB];
+        // trailing update A22 -= L21 L21' (entries with column <= row): thread (ti, tj) owns rows ti + T i', columns
+        // tj + T j' (i', j' < 4) so that neighbouring threads touch neighbouring rows (pitch 129: distinct banks)
+        if (below > 0) {
+            const int T = below >> 2;                            // 24, 16, 8
+            for (int idx = tid; idx < T * T; idx += DIAG_THREADS) {
+                const int ti = idx / T, tj = idx - ti * T;
+                if (tj > ti + 3 * T) continue;
+                const float* pr = S + (o + SB + ti) * CB_LD + o;
+                const float* pc = S + (o + SB + tj) * CB_LD + o;
+                float acc[4][4];
 #pragma unroll
-        for (int i = 0; i < SB; ++i) {
-            float s = (i == lane) ? 1.f : 0.f;
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int k = 0; k < i; ++k) s = fmaf(-S[(o + i) * CB_LD + o + k], x[k], s);
-            x[i] = (i >= lane) ? __fdiv_rn(s, S[(o + i) * CB_LD + o + i]) : 0.f;
-        }
+                    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+                for (int k = 0; k < SB; ++k) {
+                    float av[4], bv[4];
 #pragma unroll
-        for (int i = 0; i < SB; ++i) V[(o + i) * CB_LD + o + lane] = x[i];
-    }
-    __syncthreads();
-    TQ_PROF();
-    // off-diagonal sub-blocks, level by level:  V_ij = -V_ii * sum_{k=j}^{i-1} L_ik V_kj
-    for (int lev = 1; lev < NSB; ++lev) {
-        const int nblk = NSB - lev;                              // blocks (i, j) = (j + lev, j)
-        const int g = tid >> 7, t = tid & 127;                   // one 128-thread group per block
-        const int bj = g, bi = g + lev;
-        const int er = t >> 2, ec0 = (t & 3) * 8;                // each thread: row er, 8 columns
-        if (g < nblk) {
-            float acc[8];
+                    for (int i = 0; i < 4; ++i) av[i] = pr[i * T * CB_LD + k];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-            for (int k = bj * SB; k < bi * SB; ++k) {
-                const float l = S[(bi * SB + er) * CB_LD + k];
+                    for (int j = 0; j < 4; ++j) bv[j] = pc[j * T * CB_LD + k];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) acc[q] = fmaf(l, V[k * CB_LD + bj * SB + ec0 + q], acc[q]);
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int r = o + SB + ti + i * T, c = o + SB + tj + j * T;
+                        if (c <= r) S[r * CB_LD + c] -= acc[i][j];
+                    }
             }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) Tm[(g * SB + er) * (SB + 1) + ec0 + q] = acc[q];
-        }
-        __syncthreads();
-        if (g < nblk) {
-            float acc[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-            for (int k = 0; k <= er; ++k) {                      // V_ii is lower triangular
-                const float v = V[(bi * SB + er) * CB_LD + bi * SB + k];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) acc[q] = fmaf(v, Tm[(g * SB + k) * (SB + 1) + ec0 + q], acc[q]);
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) V[(bi * SB + er) * CB_LD + bj * SB + ec0 + q] = -acc[q];
         }
         __syncthreads();
         TQ_PROF();
@@ -441,7 +496,7 @@ extern "C" int tq_chol_inverse(float* Hinv, const float* Hd, int64_t m, float* w
     bool bulk_pending = false;                        // an update on `bulk` has not been joined by `st` yet
 
     static bool attr_set = false;
-    const int diag_smem = (2 * CB * CB_LD + 3 * SB * (SB + 1)) * (int)sizeof(float);
+    const int diag_smem = (2 * CB * CB_LD + SB * DG_P_LD) * (int)sizeof(float);
     if (!attr_set) {
         TQ_CUDA(cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, diag_smem));
         attr_set = true;
