@@ -47,6 +47,10 @@ constexpr int HT_GI = 28, HT_GJ = 14, HT_MAX_GROUPS = 136;
 
 struct TileSched {
     int nbi, nbj, gdim, ngroups, num_chunks;
+    int gj_tiles;                         // group width in 256-column tiles: HT_GJ, or the whole matrix when H (upper
+                                          // triangle) plus a token chunk fits L2 (m <= 4608): X is then read from DRAM once
+    int pair;                             // 1: a row index counts PAIRS of 128-row tiles (256 rows): the two CTAs of a cluster
+                                          // take the two halves and share the 256-column operand by TMA multicast
     int round_ctas, items_per_cta;        // CTA c works on items (c / round_ctas) * round_ctas * items_per_cta + c % round_ctas
                                           // + j * round_ctas, j < items_per_cta: inside a round the CTAs interleave over
                                           // consecutive items exactly like a persistent grid would (same L2 locality), but a
@@ -55,8 +59,9 @@ struct TileSched {
                                           // already complete) instead of holding every SM for the whole launch
     int tile_prefix[HT_MAX_GROUPS + 1];   // tiles in groups [0, g)
 
-    __host__ __device__ static int tiles_in_col(int bj, int bi0, int bi1) {   // valid bi in [bi0, bi1): bi <= 2*bj + 1
-        const int hi = (2 * bj + 2 < bi1) ? 2 * bj + 2 : bi1;
+    __host__ __device__ int tiles_in_col(int bj, int bi0, int bi1) const {   // valid bi in [bi0, bi1): bi <= 2*bj + 1 (pairs: bi <= bj)
+        const int lim = pair ? bj + 1 : 2 * bj + 2;
+        const int hi = (lim < bi1) ? lim : bi1;
         return hi > bi0 ? hi - bi0 : 0;
     }
     __host__ __device__ void group_rect(int g, int& bi0, int& bi1, int& bj0, int& bj1) const {
@@ -64,8 +69,9 @@ struct TileSched {
         int gj = 0, rem = g;
         while (rem > gj) { rem -= gj + 1; ++gj; }
         const int gi = rem;
-        bi0 = gi * HT_GI; bi1 = (bi0 + HT_GI < nbi) ? bi0 + HT_GI : nbi;
-        bj0 = gj * HT_GJ; bj1 = (bj0 + HT_GJ < nbj) ? bj0 + HT_GJ : nbj;
+        const int GI = pair ? gj_tiles : 2 * gj_tiles;
+        bi0 = gi * GI; bi1 = (bi0 + GI < nbi) ? bi0 + GI : nbi;
+        bj0 = gj * gj_tiles; bj1 = (bj0 + gj_tiles < nbj) ? bj0 + gj_tiles : nbj;
     }
     __host__ __device__ int group_tiles(int g) const {
         int bi0, bi1, bj0, bj1, n = 0;
@@ -94,6 +100,37 @@ struct TileSched {
     }
 };
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load delivered to the same shared-memory offset of every CTA in `mask`; each destination's mbarrier (same offset)
+// receives the complete_tx
+__device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                                      uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+// MMA completion -> arrive on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+
+// CLUSTER = 2: the two CTAs of a cluster work on the two 128-row halves of a 256 x 256 tile of H.  Both need the same
+// 256-column operand: each loads HALF of it and multicasts the boxes into both shared memories, so a CTA pulls 32 KB
+// per 64-token step through L2 -> SM instead of 48 KB (the kernel's measured limiter: 13.8 TB/s of L2 reads at 70 %
+// tensor-pipe activity).  A stage may be refilled only when BOTH CTAs have consumed it: the MMA thread's commit arrives
+// on the `empty` barrier of both CTAs (count 2).  The MMAs themselves stay cta_group::1 (one accumulator per CTA).
+template <int CLUSTER>
 __global__ void __launch_bounds__(HT_THREADS, 1)
 hessian_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_h,
                   int Nt, int kc, const __grid_constant__ TileSched sched, uint32_t idesc) {
@@ -115,7 +152,7 @@ hessian_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_h) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < HT_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < HT_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CLUSTER); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
         fence_barrier_init();
     }
@@ -124,12 +161,15 @@ hessian_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
     tc_fence_before();
     __syncthreads();
+    if (CLUSTER > 1) cluster_sync_all();             // the peer's barriers exist before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const int rank = (CLUSTER > 1) ? (int)cluster_ctarank() : 0;
+    const int unit = blockIdx.x / CLUSTER;           // the scheduling unit: a CTA, or a cluster of two
 
     const long long total_items = sched.total_items();
-    const long long item0 = (long long)(blockIdx.x / sched.round_ctas) * sched.round_ctas * sched.items_per_cta +
-                            blockIdx.x % sched.round_ctas;
+    const long long item0 = (long long)(unit / sched.round_ctas) * sched.round_ctas * sched.items_per_cta +
+                            unit % sched.round_ctas;
     const int item_stride = sched.round_ctas, my_items = sched.items_per_cta;
 
     if (warp == 0 && lane == 0) {
@@ -147,12 +187,21 @@ hessian_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 mbar_wait(empty_bar(stage), phase ^ 1);
                 const uint32_t sa = s_base + stage * HT_STAGE_BYTES;
                 const uint32_t sb = sa + HT_A_BYTES;
-                mbar_expect_tx(full_bar(stage), HT_STAGE_BYTES);
+                mbar_expect_tx(full_bar(stage), HT_STAGE_BYTES);     // own A + both halves of B (one arrives from the peer)
                 const int tok = t0 + kb * HT_BK;
+                const int bia = (CLUSTER > 1) ? 2 * bi + rank : bi;
 #pragma unroll
-                for (int c = 0; c < HT_BM / 64; ++c) tma_load_2d(sa + c * HT_BOX_BYTES, &map_x, full_bar(stage), bi * HT_BM + c * 64, tok);
+                for (int c = 0; c < HT_BM / 64; ++c) tma_load_2d(sa + c * HT_BOX_BYTES, &map_x, full_bar(stage), bia * HT_BM + c * 64, tok);
+                if (CLUSTER > 1) {
 #pragma unroll
-                for (int c = 0; c < HT_BN / 64; ++c) tma_load_2d(sb + c * HT_BOX_BYTES, &map_x, full_bar(stage), bj * HT_BN + c * 64, tok);
+                    for (int c = 0; c < HT_BN / 128; ++c) {
+                        const int box = rank * (HT_BN / 128) + c;
+                        tma_load_2d_multicast(sb + box * HT_BOX_BYTES, &map_x, full_bar(stage), bj * HT_BN + box * 64, tok, 0x3);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < HT_BN / 64; ++c) tma_load_2d(sb + c * HT_BOX_BYTES, &map_x, full_bar(stage), bj * HT_BN + c * 64, tok);
+                }
                 if (++stage == HT_STAGES) { stage = 0; phase ^= 1; }
             }
         }
@@ -182,7 +231,8 @@ hessian_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                     const uint64_t bd = make_desc(sb + k * HT_UMMA_K * 128);
                     umma_f16(tmem_d, ad, bd, idesc, (kb | k) != 0);
                 }
-                umma_commit(empty_bar(stage));          // frees the smem slot once these MMAs have read it
+                if (CLUSTER > 1) umma_commit_multicast(empty_bar(stage), 0x3);   // frees the slot in BOTH CTAs' books
+                else umma_commit(empty_bar(stage));     // frees the smem slot once these MMAs have read it
                 if (kb == nkb - 1) umma_commit(tfull_bar(acc));
                 if (++stage == HT_STAGES) { stage = 0; phase ^= 1; }
             }
@@ -224,7 +274,8 @@ hessian_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                 fence_proxy_async_smem();
                 named_bar_sync(1, 128);
                 if (leader) {
-                    tma_reduce_add_2d(&map_h, s_epi + estage * HT_EPI_BYTES, bj * HT_BN + cg * HT_EPI_COLS, bi * HT_BM);
+                    const int bia = (CLUSTER > 1) ? 2 * bi + rank : bi;
+                    tma_reduce_add_2d(&map_h, s_epi + estage * HT_EPI_BYTES, bj * HT_BN + cg * HT_EPI_COLS, bia * HT_BM);
                     bulk_commit();
                 }
                 estage ^= 1;
@@ -238,6 +289,7 @@ hessian_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     if (warp == 2) {
         tmem_dealloc_512(tmem_base);
     }
+    if (CLUSTER > 1) cluster_sync_all();             // neither CTA leaves while the other may still signal its barriers
 }
 
 // ---- host side ---------------------------------------------------------------------------------
@@ -285,10 +337,15 @@ int hessian_accum_tcgen05(float* H, int64_t ldh, const void* X, int64_t Nt, int6
     if ((rc = make_tmap_2d(&map_h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, H, m, m, ldh, HT_BM, HT_EPI_COLS, "tq_hessian_accum(H)")))
         return rc;
 
+    // TQ_HESS_CLUSTER=1 selects the single-CTA kernel (48 KB of operands per step and CTA instead of 32 KB)
+    static const int cluster = []() { const char* e = getenv("TQ_HESS_CLUSTER"); return (e && atoi(e) == 1) ? 1 : 2; }();
     TileSched sched;
-    sched.nbi = (int)ceil_div(m, HT_BM);
+    sched.pair = (cluster == 2) ? 1 : 0;
+    sched.nbi = (int)ceil_div(ceil_div(m, HT_BM), cluster);
     sched.nbj = (int)ceil_div(m, HT_BN);
-    sched.gdim = (int)ceil_div(sched.nbj, HT_GJ);
+    static const int one_group_max = []() { const char* e = getenv("TQ_HESS_ONE_GROUP_MAX_M"); return e ? atoi(e) : 4608; }();
+    sched.gj_tiles = (m <= one_group_max) ? sched.nbj : HT_GJ;
+    sched.gdim = (int)ceil_div(sched.nbj, sched.gj_tiles);
     sched.ngroups = sched.gdim * (sched.gdim + 1) / 2;
     TQ_CHECK_ARG(sched.ngroups <= HT_MAX_GROUPS, "tq_hessian_accum: m = %lld is beyond the scheduler's group table", (long long)m);
     sched.tile_prefix[0] = 0;
@@ -301,7 +358,7 @@ int hessian_accum_tcgen05(float* H, int64_t ldh, const void* X, int64_t Nt, int6
     // TQ_HESS_SPARE_SMS: SMs this persistent kernel leaves to the chains of other linears (inverse / sweep kernels on other
     // streams) that run while the remaining Hessians of the layer are still being accumulated
     static const int spare = []() { const char* e = getenv("TQ_HESS_SPARE_SMS"); return e ? atoi(e) : 0; }();
-    const int sms = (sm_count() - spare > 16) ? sm_count() - spare : sm_count();
+    const int sms = ((sm_count() - spare > 16) ? sm_count() - spare : sm_count()) / cluster;   // scheduling units per round
     int64_t kc_l2 = (40ll << 20) / (2 * (m < 7168 ? m : 7168));
     kc_l2 = (kc_l2 / HT_BK) * HT_BK;
     if (kc_l2 < 256) kc_l2 = 256;
@@ -322,10 +379,12 @@ int hessian_accum_tcgen05(float* H, int64_t ldh, const void* X, int64_t Nt, int6
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) |
                            ((uint32_t)(HT_BN >> 3) << 17) | ((uint32_t)(HT_BM >> 4) << 24);
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        TQ_CUDA(cudaFuncSetAttribute(hessian_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM));
-        attr_set = true;
+    static std::atomic<unsigned long long> attr_mask{0};
+    int dev;
+    if (dyn_smem_pending(attr_mask, dev)) {
+        TQ_CUDA(cudaFuncSetAttribute(hessian_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM));
+        TQ_CUDA(cudaFuncSetAttribute(hessian_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM));
+        dyn_smem_done(attr_mask, dev);
     }
     // TQ_HESS_ITEMS_PER_CTA: work items (one <= 2048-token chunk of one 128 x 256 tile, ~9 us) a CTA processes before it
     // retires; 0 = persistent (one CTA per SM for the whole launch)
@@ -333,8 +392,24 @@ int hessian_accum_tcgen05(float* H, int64_t ldh, const void* X, int64_t Nt, int6
     sched.round_ctas = (int)((items < sms) ? items : sms);
     const int64_t per_cta_persistent = ceil_div(items, sched.round_ctas);
     sched.items_per_cta = (int)((ipc_env > 0 && ipc_env < per_cta_persistent) ? ipc_env : per_cta_persistent);
-    const int grid = (int)(ceil_div(items, (int64_t)sched.round_ctas * sched.items_per_cta) * sched.round_ctas);
-    hessian_tc_kernel<<<grid, HT_THREADS, HT_SMEM, st>>>(map_x, map_h, (int)Nt, (int)kc, sched, idesc);
+    const int grid = (int)(ceil_div(items, (int64_t)sched.round_ctas * sched.items_per_cta) * sched.round_ctas) * cluster;
+    if (cluster == 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(HT_THREADS);
+        cfg.dynamicSmemBytes = HT_SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        TQ_CUDA(cudaLaunchKernelEx(&cfg, hessian_tc_kernel<2>, map_x, map_h, (int)Nt, (int)kc, sched, idesc));
+    } else {
+        hessian_tc_kernel<1><<<grid, HT_THREADS, HT_SMEM, st>>>(map_x, map_h, (int)Nt, (int)kc, sched, idesc);
+    }
     TQ_LAUNCH_CHECK("hessian_tc_kernel");
     return 0;
 }

@@ -75,29 +75,51 @@ def same_block_membership(perm_a, perm_b, block_size=128):
                for k in range(0, a.shape[0], block_size))
 
 
+_MODEL_FLOOR = None
+
+
+def model_level_tolerances(name):
+    """(codes, alpha, mu) tolerances for one linear of a whole-model run, DERIVED from the reference's own run-to-run
+    floor (tests/golden/model_toy_floor.json, written by make_golden_model_floor.py: the unmodified reference's
+    quantize() with all host threads vs one thread).  Per layer index: codes >= 1 - 4 x (1 - floor agreement), never
+    looser than north_star's 0.999 would be if the floor allowed it; scales <= 5 x the floor's scale error and at least
+    north_star's 1e-4.  The floor is taken over both sweep orders (the fixture holds SSR for layer 0 only)."""
+    global _MODEL_FLOOR
+    if _MODEL_FLOOR is None:
+        import json
+        import os
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "model_toy_floor.json")) as fh:
+            _MODEL_FLOOR = json.load(fh)
+    layer = name.split(".")[0]
+    rows = [_MODEL_FLOOR[tag][layer] for tag in ("seq", "ssr") if layer in _MODEL_FLOOR.get(tag, {})]
+    if not rows:                                   # deeper layers than the fixture has: the last recorded layer's floor
+        rows = [_MODEL_FLOOR["seq"][sorted(_MODEL_FLOOR["seq"])[-1]]]
+    code_floor = min(r["code_agreement_min"] for r in rows)
+    a_floor = max(r["alpha_rel_err_max"] for r in rows)
+    u_floor = max(r["mu_err_rel_alpha_max"] for r in rows)
+    return min(CODE_AGREEMENT, 1.0 - 4.0 * (1.0 - code_floor)), max(SCALE_RTOL, 5.0 * a_floor), max(SCALE_RTOL, 5.0 * u_floor)
+
+
 def assert_model_level_parity(name, got, ref):
     """Parity of one linear quantised inside a whole-model run (PT2LLMQuantizer.quantize) against the reference's run.
 
-    Layer 0 sees bit-identical inputs on both sides: same block membership, north_star code agreement, scales to 5e-4
-    (the single-layer bar is 1e-4; here the AGA Gram comes out of a different GEMM on each side -- numpy / the CUDA SYRK
-    / MKL sgemm -- and alpha of a few rows moves by ~1.2e-4).  Layer 1's inputs went through layer 0's quantised
-    weights, and the block sweep amplifies 1e-6 input differences into code flips at thresholds: the REFERENCE AGAINST
-    ITSELF (8 vs 1 MKL threads, same inputs) agrees on 0.9957 .. 0.9994 of layer 1's codes (0.99997 .. 1.0 on layer 0),
-    so layer 1 is held to that floor with margin: >= 0.985 of the codes (CUDA path vs reference on a B200: 0.9917 ..
-    0.9988), scales of agreeing (row, block) pairs within 1e-2."""
-    first = name.startswith("layer_0.")
+    Layer 0 sees bit-identical inputs on both sides; layer 1's inputs went through layer 0's quantised weights, and the
+    block sweep amplifies 1e-6 input differences into code flips at thresholds.  The tolerances are not asserted by
+    hand: they come from the REFERENCE AGAINST ITSELF (model_level_tolerances): all host threads vs one thread it
+    agrees on 0.99994 .. 0.99997 of layer 0's codes with scales to 4.5e-5 (sequential) / 1.2e-4 (SSR), and on 0.9957 of
+    layer 1's codes with scales to 3.5e-3."""
+    tol_codes, tol_alpha, tol_mu = model_level_tolerances(name)
     assert same_block_membership(got["perm"], ref["perm"]), f"{name}: block membership differs"
     agree = code_agreement(got["T"], ref["T"])
-    assert agree >= (CODE_AGREEMENT if first else 0.985), f"{name}: code agreement {agree:.6f}"
+    assert agree >= tol_codes, f"{name}: code agreement {agree:.6f} < {tol_codes:.6f}"
     mask = block_pairs_agree(got["T"], ref["T"], ref["perm"], 128)
     finite = np.isfinite(np.asarray(ref["alpha"], dtype=np.float64)) & (np.abs(np.asarray(ref["alpha"], dtype=np.float64)) < 1e3)
     mask &= finite                           # rows the reference's AGA blew up (SURVEY Q9) carry ~1e14 scales on both sides
     assert mask.mean() > 0.5, name
     ea = scale_rel_err(got["alpha"], ref["alpha"], mask)
-    assert ea <= (5e-4 if first else 1e-2), f"{name}: alpha rel err {ea:.3e}"
-    if first:
-        em = scale_rel_err(got["mu"], ref["mu"], mask, floor=np.abs(np.asarray(ref["alpha"], dtype=np.float64)))
-        assert em <= 5e-4, f"{name}: mu err (relative to alpha) {em:.3e}"
+    assert ea <= tol_alpha, f"{name}: alpha rel err {ea:.3e} > {tol_alpha:.3e}"
+    em = scale_rel_err(got["mu"], ref["mu"], mask, floor=np.abs(np.asarray(ref["alpha"], dtype=np.float64)))
+    assert em <= tol_mu, f"{name}: mu err (relative to alpha) {em:.3e} > {tol_mu:.3e}"
     return agree
 
 
