@@ -681,9 +681,12 @@ def main():
         for li in range(cfg["layers"]):
             if world > 1:
                 # per layer: local Hessians -> NCCL all-reduce -> inverses dealt to ranks + broadcast -> row-slab sweeps
+                ph = [] if (record and li == cfg["layers"] - 1) else None
                 results_keep["last"] = sharded_layer.quantize(
                     [(name, weights[li][name], acts[src]) for name, n, m, src in lins], use_ssr=use_ssr, order=order,
-                    hess_timing=hess_events if record else None)
+                    hess_timing=hess_events if record else None, phases=ph)
+                if ph is not None:
+                    results_keep["phases"] = ph
                 continue
             if os.environ.get("BENCH_DEBUG"):
                 torch.cuda.synchronize()
@@ -726,6 +729,21 @@ def main():
         ms = float(t.item())
     ms_per_step = ms / args.steps
     value = ms_per_step / 1e3
+
+    # N > 1: critical-path breakdown of the last timed layer on every rank (ms since the layer's start), gathered on rank 0
+    breakdown = None
+    if world > 1 and results_keep.get("phases"):
+        ph = results_keep["phases"]
+        mine = {tag: ph[0][1].elapsed_time(ev) for tag, ev in ph[1:]}
+        tags = ["hessians", "reduce", "split_inverse", "split_bcast", "split_sweep", "own_chains"]
+        row = torch.tensor([mine.get(tg, -1.0) for tg in tags], device=dev)
+        rows = [torch.empty_like(row) for _ in range(world)]
+        dist.all_gather(rows, row)
+        breakdown = {"unit": "ms since the layer's first kernel, last timed layer, per rank", "tags": tags,
+                     "ranks": [[round(float(x), 3) for x in r.tolist()] for r in rows],
+                     "note": "hessians: local SYRKs done; reduce: NCCL reduce / all-reduce of every H done; split_inverse: the "
+                             "owner's damped inverse of a row-split linear done (-1 on the other ranks); split_bcast: its H^-1 "
+                             "received; split_sweep: this rank's row slab of it swept; own_chains: this rank's whole linears done"}
 
     # roofline of the dominant kernel (hessian_tc_kernel), live CUDA-event timing per launch
     flops = sum(hessian_useful_flops(t_, m_) for _, _, t_, m_ in hess_events)
@@ -878,6 +896,8 @@ def main():
                 "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": workload_config(args), "clocks": clocks,
                 "gpu_launches": int(launches), "roofline": roofline, "e2e": e2e}
+        if breakdown is not None:
+            line["critical_path"] = breakdown
         if cfg["layers"] != full_layers:
             line["config"]["workload"] += f" [DEBUG: only {cfg['layers']} of {full_layers} layers]"
         if n1 is not None:

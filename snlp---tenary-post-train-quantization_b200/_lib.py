@@ -65,6 +65,9 @@ _SIGNATURES = {
     "tq_comm_ready": (_int, []),
     "tq_comm_destroy": (_int, []),
     "tq_comm_allreduce_f32": (_int, [_ptr, _i64, _ptr]),
+    "tq_comm_p2p_alloc": (_int, [_i64, _int, _int, _ptr]),
+    "tq_comm_p2p_open": (_int, [_ptr]),
+    "tq_comm_p2p_ready": (_int, []),
 }
 
 EXPORTS = tuple(_SIGNATURES)

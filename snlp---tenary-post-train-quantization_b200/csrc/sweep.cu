@@ -20,6 +20,8 @@ int launch_unpermute(const int8_t*, int64_t, int64_t, const int32_t*, int8_t*, f
 int launch_ssr_fold(const float*, int64_t, const float*, int64_t, int64_t, float*, cudaStream_t);
 bool comm_active();
 int comm_allreduce_sum_f32(float*, int64_t, cudaStream_t);
+bool p2p_active();
+int p2p_fold_allreduce(const float*, int64_t, const float*, int64_t, int64_t, float*, cudaStream_t);
 
 __global__ void iota_kernel(int32_t* __restrict__ a, int m) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -92,8 +94,8 @@ extern "C" int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const
                  "tq_sweep_layer: AGA mode %d needs its Hessian (Hd for HESSIAN, Hraw for ACTIVATIONS)", aga);
     TQ_CHECK_ARG(max_iter >= 0, "tq_sweep_layer: max_iter < 0");
     const bool sharded = (flags & TQ_SWEEP_ROW_SHARD) != 0;
-    TQ_CHECK_ARG(!sharded || order != TQ_ORDER_SSR || comm_active(),
-                 "tq_sweep_layer: TQ_SWEEP_ROW_SHARD with SSR needs the communicator (tq_comm_init)");
+    TQ_CHECK_ARG(!sharded || order != TQ_ORDER_SSR || comm_active() || p2p_active(),
+                 "tq_sweep_layer: TQ_SWEEP_ROW_SHARD with SSR needs the communicator (tq_comm_init) or peer mailboxes");
     cudaStream_t st = (cudaStream_t)stream;
     SweepWs ws = carve(workspace, n, m, block);
     if (ws.bytes > workspace_bytes) {
@@ -157,8 +159,13 @@ extern "C" int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const
                 }
                 if (sharded) {
                     // rows are one shard of the layer: column statistics must cover every shard's rows
-                    if ((rc = launch_ssr_fold(ws.partials, chunks, ws.rowmean, n, rem, ws.folded, st))) return rc;
-                    if ((rc = comm_allreduce_sum_f32(ws.folded, 2 * rem + 1, st))) return rc;
+                    if (p2p_active()) {
+                        // fold + exchange through peer memory (one-shot all-reduce, comm.cu)
+                        if ((rc = p2p_fold_allreduce(ws.partials, chunks, ws.rowmean, n, rem, ws.folded, st))) return rc;
+                    } else {
+                        if ((rc = launch_ssr_fold(ws.partials, chunks, ws.rowmean, n, rem, ws.folded, st))) return rc;
+                        if ((rc = comm_allreduce_sum_f32(ws.folded, 2 * rem + 1, st))) return rc;
+                    }
                     if ((rc = launch_ssr_select(ws.folded, 1, nullptr, n, ws.folded + 2 * rem, ws.rem[cur], rem, block,
                                                 perm + done, ws.rem[cur ^ 1], ws.sims,
                                                 reinterpret_cast<uint32_t*>(ws.sims + m), st)))

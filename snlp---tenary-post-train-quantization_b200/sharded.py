@@ -59,6 +59,38 @@ def init_comm(ctx: ShardContext):
     cbuf = (ctypes.c_ubyte * 128).from_buffer_copy(raw)
     with torch.cuda.device(ctx.device):
         _lib.check(lib.tq_comm_init(cbuf, ctx.rank, ctx.world), "tq_comm_init")
+    init_p2p(ctx)
+
+
+def init_p2p(ctx: ShardContext, cap_floats: int = 2 * 32768 + 16):
+    """Open the peer-memory mailboxes of the one-shot all-reduce (csrc/comm.cu): every rank allocates its buffer, the
+    CUDA IPC handles are all-gathered, every rank maps the others'.  Falls back to NCCL (returns False) when the
+    ranks cannot map each other's memory (TQ_P2P_ALLREDUCE=0 forces that)."""
+    import ctypes
+    import os
+    lib = _lib.load()
+    if ctx.world == 1 or lib.tq_comm_p2p_ready():
+        return bool(lib.tq_comm_p2p_ready())
+    if os.environ.get("TQ_P2P_ALLREDUCE", "1") == "0" or ctx.world > 16:
+        return False
+    handle = (ctypes.c_ubyte * 64)()
+    with torch.cuda.device(ctx.device):
+        ok = lib.tq_comm_p2p_alloc(int(cap_floats), ctx.rank, ctx.world, handle) == 0
+    mine = torch.tensor(list(handle) + [1 if ok else 0], dtype=torch.uint8, device=ctx.device)
+    every = [torch.empty_like(mine) for _ in range(ctx.world)]
+    dist.all_gather(every, mine, group=ctx.group)
+    every = [t.cpu() for t in every]
+    if not all(int(t[64]) == 1 for t in every):
+        return False
+    raw = b"".join(bytes(t[:64].tolist()) for t in every)
+    buf = (ctypes.c_ubyte * len(raw)).from_buffer_copy(raw)
+    with torch.cuda.device(ctx.device):
+        opened = lib.tq_comm_p2p_open(buf) == 0
+    flag = torch.tensor([1 if opened else 0], dtype=torch.int32, device=ctx.device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=ctx.group)
+    if int(flag.item()) != 1:
+        raise RuntimeError("peer mailboxes opened on some ranks only: set TQ_P2P_ALLREDUCE=0 to use NCCL for the exchange")
+    return True
 
 
 class ShardedGPTQ:
@@ -163,10 +195,18 @@ class ShardedLayer:
             owner = [(-1 - o) if chain_cost(*s) > self.split_threshold * fair else o for o, s in zip(owner, shapes)]
         return owner
 
-    def _quantize_by_linear(self, linears, use_ssr, aga, max_iter, hess_timing, order=None):
+    def _quantize_by_linear(self, linears, use_ssr, aga, max_iter, hess_timing, order=None, phases=None):
         ctx = self.ctx
         use_ssr = (order == "ssr") if order is not None else use_ssr
         main = torch.cuda.current_stream(ctx.device)
+
+        def mark(tag, stream=None):
+            # critical-path breakdown (bench): timing events on the stream a phase ends on
+            if phases is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record(stream if stream is not None else main)
+                phases.append((tag, ev))
+        mark("start")
         owner = self.owners([_shape_of(W) for _, W, _ in linears])
         split = [i for i, o in enumerate(owner) if o < 0]
         if split and use_ssr and not _lib.comm_ready():
@@ -182,6 +222,7 @@ class ShardedLayer:
                 e1.record()
                 hess_timing.append((e0, e1, X.numel() // X.shape[-1], X.shape[-1]))
             states.append(st)
+        mark("hessians")
         if ctx.world > 1:
             counts = torch.tensor([st.nsamples for st in states], dtype=torch.int64, device=ctx.device)
             dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=ctx.group)
@@ -194,6 +235,7 @@ class ShardedLayer:
             for st, c in zip(states, counts.tolist()):
                 st.nsamples = int(c)
                 st._cache.clear()
+        mark("reduce")
         # split linears first on their owner: the inverse is the longest single dependent chain of the layer
         pending = {}
         if split:
@@ -207,6 +249,7 @@ class ShardedLayer:
                         Hd, Hinv, info = st.damped_inverse(self.percdamp)
                         done = torch.cuda.Event()
                         done.record(self._inv_stream)
+                        mark("split_inverse", self._inv_stream)
                 else:
                     Hd = st.damped(self.percdamp)
                     Hinv = torch.empty((m, m), dtype=torch.float32, device=ctx.device)
@@ -237,14 +280,17 @@ class ShardedLayer:
             src = -1 - owner[i]
             dist.broadcast(Hinv, src=src, group=ctx.group)
             dist.broadcast(info, src=src, group=ctx.group)
+            mark("split_bcast")
             st._cache[float(self.percdamp)] = (Hd, Hinv, info)
             st._cache_events.pop(float(self.percdamp), None)
             lo, hi = ctx.row_range(W.shape[0])
             g = GPTQ(LinearView(W[lo:hi]), self.block_size, self.percdamp, hessian=st)
             g.sweep_flags = _lib.SWEEP_ROW_SHARD
             g.quantize(use_ssr=use_ssr, aga=aga, max_iter=max_iter, order=order)
+            mark("split_sweep")
             slabs[i] = (g, (lo, hi))
         self._driver.finish_chains(gs, chain_seq)
+        mark("own_chains")
         out = []
         done_whole = dict(zip(mine, gs))
         for i, (name, W, _) in enumerate(linears):
@@ -259,8 +305,10 @@ class ShardedLayer:
         return out
 
     def quantize(self, linears, use_ssr: bool = True, aga: str = "hessian", max_iter: int = 100, hess_timing=None,
-                 order: Optional[str] = None):
+                 order: Optional[str] = None, phases=None):
         """linears: [(name, W (n, m), X_local (this rank's samples, (.., m)))].  ``order`` as in GPTQ.quantize.
+        phases (mode 'linears'): optional list that receives (tag, timing event) marks of the layer's critical path --
+        start, hessians, reduce, split_inverse (owner only), split_bcast, split_sweep, own_chains.
         mode 'linears': W is read only on the linear's owner (see owners()); other ranks may pass its (n, m) shape instead;
           returns [(name, alpha, mu, T_int8, perm, (0, n))] with None tensors and rows (0, 0) for linears owned elsewhere;
           a *split* linear (owners() < 0) needs W on every rank (only this rank's row slab is read) and returns row slabs.
@@ -268,7 +316,7 @@ class ShardedLayer:
           [(name, alpha_slab, mu_slab, T_int8_slab, perm, (row_lo, row_hi))] in the input order.
         hess_timing: optional list that receives (start_event, end_event, tokens, m) per Hessian launch."""
         if self.mode == "linears":
-            return self._quantize_by_linear(linears, use_ssr, aga, max_iter, hess_timing, order)
+            return self._quantize_by_linear(linears, use_ssr, aga, max_iter, hess_timing, order, phases)
         ctx = self.ctx
         sweep_order = order
         main = torch.cuda.current_stream(ctx.device)

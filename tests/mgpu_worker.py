@@ -24,6 +24,9 @@ def main():
     ctx = sharded.ShardContext(rank, world, dev)
     sharded.init_comm(ctx)
     assert tq100._lib.comm_ready()
+    p2p = tq100._lib.load().tq_comm_p2p_ready()
+    print(f"[mgpu] rank {rank}: peer mailboxes open for {p2p} ranks", flush=True)
+    assert (p2p == world) == (os.environ.get("TQ_EXPECT_P2P", "1") == "1"), p2p
 
     samples, seq = 8, 256
     shapes = [("a", 512, 1024), ("b", 384, 1024), ("c", 1024, 640)]
