@@ -410,46 +410,66 @@ def reference_cuda_leg(torch, args, cfg, order, lins, w0, acts, driver, dev):
 
 
 def sharded_parity_leg(torch, dist, tq100, args, ctx, order, lins, w_last, acts, sharded_out, sharded_layer):
-    """N > 1: the sharded run's results of the last timed layer against the plain single-GPU path on the same inputs --
-    every rank all-reduces the local Hessians of one whole-owner linear (o_proj) and of down_proj (split by rows from 4
-    GPUs up), quantises them with the single-GPU GPTQ and compares ITS part of the sharded output; minima over ranks."""
+    """N > 1: the sharded run's results of the last timed layer against the plain single-GPU path on the same inputs.
+    For one whole-owner linear (o_proj) and for down_proj (split by rows from 4 GPUs up) the local Hessians are reduced
+    exactly as the sharded path reduces them (NCCL reduce onto the owner / all-reduce for a split linear), the ranks
+    that hold results quantise the linear with the single-GPU GPTQ and compare THEIR part of the sharded output: sweep
+    order, codes (over the leading blocks whose membership agrees -- one swapped SSR top-k boundary legitimately
+    de-correlates what follows), scales on rows whose codes agree.  Minima / maxima over the ranks that compared."""
     from tq100.pipeline import LinearView
     from tq100.gptq import GPTQ, HessianState
     dev = ctx.device
-    rep = {"against": "single-GPU GPTQ.quantize on the all-reduced Hessian, same weights", "linears": {}}
+    owners = sharded_layer.owners([(a_, b_) for _, a_, b_, _ in lins]) if sharded_layer.mode == "linears" else [-1] * len(lins)
+    rep = {"against": "single-GPU GPTQ.quantize on the same NCCL-reduced Hessian and weights", "linears": {}}
     for name in ("o_proj", "down_proj"):
         i = [l[0] for l in lins].index(name)
         _, n, m, src = lins[i]
         st = HessianState(m, dev)
         st.add_batch(acts[src])
         H = st.full()
-        dist.all_reduce(H)
+        split = owners[i] < 0
+        if split:
+            dist.all_reduce(H)
+        else:
+            dist.reduce(H, dst=owners[i])
         cnt = torch.tensor([st.nsamples], dtype=torch.int64, device=dev)
         dist.all_reduce(cnt)
         st.nsamples = int(cnt.item())
         st._cache.clear()
-        g = GPTQ(LinearView(w_last[name]), 128, 0.01, hessian=st)
-        g.quantize(use_ssr=order == "ssr", order=order)
         _, a, u, T8, perm, (lo, hi) = sharded_out[i]
-        stats = torch.tensor([1.0, 1.0, 0.0, 0.0], dtype=torch.float64, device=dev)   # min code, perm equal, max alpha err, rows
+        # code agreement, leading blocks, blocks, perm equal, alpha err, rows  (neutral element where this rank holds nothing)
+        lo_stats = torch.tensor([1.0, 1e9, 1e9, 1.0], dtype=torch.float64, device=dev)       # reduced with MIN
+        hi_stats = torch.tensor([0.0, 0.0], dtype=torch.float64, device=dev)                 # reduced with MAX / SUM
         if a is not None and hi > lo:
-            same = (T8 == g.T_int8[lo:hi])
-            pe = bool(torch.equal(perm.long(), g.perm.long()))
-            clean = same.all(dim=1)
-            aerr = ((a.float() - g.alpha[lo:hi].float()).abs() / g.alpha[lo:hi].float().abs().clamp(min=1e-12))[clean]
-            stats = torch.tensor([float(same.float().mean()), 1.0 if pe else 0.0,
-                                  float(aerr.max()) if aerr.numel() else 0.0, float(hi - lo)], dtype=torch.float64, device=dev)
-        mn = stats.clone()
-        dist.all_reduce(mn, op=dist.ReduceOp.MIN)
-        mx = stats.clone()
+            g = GPTQ(LinearView(w_last[name]), 128, 0.01, hessian=st)
+            g.quantize(use_ssr=order == "ssr", order=order)
+            nb = (m + 127) // 128
+            ps, pg = perm.long(), g.perm.long()
+            lead = 0
+            for k in range(nb):
+                if not torch.equal(torch.sort(ps[k * 128:(k + 1) * 128]).values, torch.sort(pg[k * 128:(k + 1) * 128]).values):
+                    break
+                lead += 1
+            cols = pg[:lead * 128]
+            same = (T8[:, cols] == g.T_int8[lo:hi][:, cols]) if lead else torch.zeros((1, 1), dtype=torch.bool, device=dev)
+            clean = same.all(dim=1) if lead else torch.zeros(1, dtype=torch.bool, device=dev)
+            ga = g.alpha[lo:hi, :lead].float()
+            aerr = ((a[:, :lead].float() - ga).abs() / ga.abs().clamp(min=1e-12))[clean] if lead else torch.zeros(0, device=dev)
+            lo_stats = torch.tensor([float(same.float().mean()), float(lead), float(nb), 1.0 if torch.equal(ps, pg) else 0.0],
+                                    dtype=torch.float64, device=dev)
+            hi_stats = torch.tensor([float(aerr.max()) if aerr.numel() else 0.0, float(hi - lo)], dtype=torch.float64, device=dev)
+        dist.all_reduce(lo_stats, op=dist.ReduceOp.MIN)
+        mx = hi_stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = stats.clone()
+        sm = hi_stats.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        rep["linears"][name] = {"shape": [n, m], "min_code_agreement_over_ranks": float(mn[0]), "perm_equal_on_every_rank": bool(mn[1] == 1.0),
-                                "max_alpha_rel_err_on_rows_with_equal_codes": float(mx[2]), "rows_compared": int(sm[3]),
-                                "split_by_rows": bool(sharded_layer.mode == "rows" or
-                                                      sharded_layer.owners([(a_, b_) for _, a_, b_, _ in lins])[i] < 0)}
-    rep["ok"] = all(v["min_code_agreement_over_ranks"] >= 0.999 for v in rep["linears"].values())
+        rep["linears"][name] = {"shape": [n, m], "split_by_rows": bool(split),
+                                "min_code_agreement_on_leading_blocks": float(lo_stats[0]),
+                                "leading_blocks_same_membership": int(lo_stats[1]), "blocks": int(lo_stats[2]),
+                                "sweep_order_equal_on_every_rank": bool(lo_stats[3] == 1.0),
+                                "max_alpha_rel_err_on_rows_with_equal_codes": float(mx[0]), "rows_compared": int(sm[1])}
+    rep["ok"] = all(v["min_code_agreement_on_leading_blocks"] >= 0.999 and v["leading_blocks_same_membership"] >= 1
+                    for v in rep["linears"].values())
     return rep
 
 
@@ -605,6 +625,9 @@ def main():
     ap.add_argument("--streams", type=int, default=4, help="CUDA streams the per-linear prologue+sweep chains are spread over")
     ap.add_argument("--shard-mode", default="linears", choices=["linears", "rows"],
                     help="N > 1: deal whole linears to ranks (default) or row-shard every linear (SSR statistics all-reduced)")
+    ap.add_argument("--split-threshold", type=float, default=1.5,
+                    help="N > 1, --shard-mode linears: a linear whose chain exceeds this multiple of a rank's fair share is "
+                         "split by rows (default 1.5: down_proj from 4 GPUs up)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-shared", action="store_true", help="skip the secondary shared-Hessian (N1) measurement")
@@ -673,7 +696,8 @@ def main():
 
     if world > 1:
         par.init_comm(ctx)
-    sharded_layer = par.ShardedLayer(ctx, block_size=128, percdamp=0.01, mode=args.shard_mode, num_streams=args.streams)
+    sharded_layer = par.ShardedLayer(ctx, block_size=128, percdamp=0.01, mode=args.shard_mode, num_streams=args.streams,
+                                     split_threshold=args.split_threshold)
     from tq100.pipeline import LayerDriver
     driver = LayerDriver(dev, block_size=128, percdamp=0.01, num_streams=args.streams)
 

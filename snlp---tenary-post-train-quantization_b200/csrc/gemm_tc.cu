@@ -585,41 +585,47 @@ split_kernel(const float* __restrict__ in, int64_t ld_in, int rows, int cols, fl
 
 // B operand of the error feedback, K-major:  coef[j][i] = Hinv[blk_i, rem_j] / clamp(Hinv[blk_i, blk_i], 1e-8)
 // (gptq.py:173-181), written as hi/lo.  Reads walk rem_j (ascending, near-contiguous) along rows blk_i of Hinv.
+constexpr int COEF_SPAN = 4;          // 32-position sub-tiles per CTA: one partial of C 1 per 128 remaining positions
 __global__ void __launch_bounds__(256)
 feedback_coef_kernel(const float* __restrict__ Hinv, int64_t ldh, const int32_t* __restrict__ blk_idx, int blk0, int b,
                      const int32_t* __restrict__ rem_idx, int rem0, int rem, float* __restrict__ hi,
                      float* __restrict__ lo, int64_t ldb, float* __restrict__ csum_part) {
     __shared__ float tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int j0 = blockIdx.x * 32, i0 = blockIdx.y * 32;
-    for (int ii = ty; ii < 32; ii += 8) {
-        const int i = i0 + ii, j = j0 + tx;
-        float v = 0.f;
-        if (i < b && j < rem) {
-            const int bc = blk_idx ? blk_idx[i] : blk0 + i;
-            const int rc = rem_idx ? rem_idx[j] : rem0 + j;
-            const float* hrow = Hinv + (int64_t)bc * ldh;
-            v = __fdiv_rn(hrow[rc], fmaxf(hrow[bc], kTiny));
+    const int i0 = blockIdx.y * 32;
+    float csum = 0.f;                                     // ty == 0: sum over this CTA's positions of C[i0 + tx, j]
+    for (int sp = 0; sp < COEF_SPAN; ++sp) {
+        const int j0 = (blockIdx.x * COEF_SPAN + sp) * 32;
+        if (j0 >= rem) break;                             // CTA-uniform
+        for (int ii = ty; ii < 32; ii += 8) {
+            const int i = i0 + ii, j = j0 + tx;
+            float v = 0.f;
+            if (i < b && j < rem) {
+                const int bc = blk_idx ? blk_idx[i] : blk0 + i;
+                const int rc = rem_idx ? rem_idx[j] : rem0 + j;
+                const float* hrow = Hinv + (int64_t)bc * ldh;
+                v = __fdiv_rn(hrow[rc], fmaxf(hrow[bc], kTiny));
+            }
+            tile[ii][tx] = v;
         }
-        tile[ii][tx] = v;
-    }
-    __syncthreads();
-    if (csum_part != nullptr && ty == 0) {
-        // sum over this CTA's 32 remaining positions of C[i, j], for its 32 block columns i (fixed order)
-        float s = 0.f;
+        __syncthreads();
+        if (csum_part != nullptr && ty == 0) {
+            // fixed order: position by position inside the sub-tile, sub-tile by sub-tile
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) s += tile[tx][jj];
-        if (i0 + tx < b) csum_part[(int64_t)blockIdx.x * b + i0 + tx] = s;
-    }
-    for (int jj = ty; jj < 32; jj += 8) {
-        const int j = j0 + jj, i = i0 + tx;
-        if (j < rem && i < b) {
-            float h, l;
-            split_tf32(tile[tx][jj], h, l);
-            hi[(int64_t)j * ldb + i] = h;
-            lo[(int64_t)j * ldb + i] = l;
+            for (int jj = 0; jj < 32; ++jj) csum += tile[tx][jj];
         }
+        for (int jj = ty; jj < 32; jj += 8) {
+            const int j = j0 + jj, i = i0 + tx;
+            if (j < rem && i < b) {
+                float h, l;
+                split_tf32(tile[tx][jj], h, l);
+                hi[(int64_t)j * ldb + i] = h;
+                lo[(int64_t)j * ldb + i] = l;
+            }
+        }
+        __syncthreads();
     }
+    if (csum_part != nullptr && ty == 0 && i0 + tx < b) csum_part[(int64_t)blockIdx.x * b + i0 + tx] = csum;
 }
 
 int launch_split(const float* in, int64_t ld_in, int64_t rows, int64_t cols, float* hi, float* lo, int64_t ld_out,
@@ -757,7 +763,7 @@ int launch_gemm_tf32x3(int mode, float* C, int64_t ldc, int64_t M, int64_t N, in
 int launch_feedback_coef(const float* Hinv, int64_t ldh, const int32_t* blk_idx, int64_t blk0, int64_t b,
                          const int32_t* rem_idx, int64_t rem0, int64_t rem, float* ch, float* cl, int64_t ldb,
                          float* csum_part, cudaStream_t st) {
-    dim3 grid((unsigned)ceil_div(rem, 32), (unsigned)ceil_div(b, 32));
+    dim3 grid((unsigned)ceil_div(rem, 32 * COEF_SPAN), (unsigned)ceil_div(b, 32));
     feedback_coef_kernel<<<grid, 256, 0, st>>>(Hinv, ldh, blk_idx, (int)blk0, (int)b, rem_idx, (int)rem0, (int)rem, ch, cl, ldb,
                                                csum_part);
     TQ_LAUNCH_CHECK("feedback_coef_kernel");

@@ -154,7 +154,6 @@ __global__ void __launch_bounds__(SEL_THREADS)
 ssr_select_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__ rem_idx, int rem, int block,
                   int32_t* __restrict__ blk_idx, int32_t* __restrict__ new_rem_idx) {
     __shared__ int wsum[33];
-    __shared__ int hist[256];
     __shared__ int whist[SEL_THREADS / 32][256];   // one histogram per warp: similarities of one layer share their leading
                                                    // key bytes, so a single shared histogram serialises ~rem atomics on ONE
                                                    // address per pass (measured 26 us per selection at rem = 11008)
@@ -175,27 +174,34 @@ ssr_select_kernel(const uint32_t* __restrict__ keys, const int32_t* __restrict__
                 const uint32_t k = keys[j];
                 const bool in = (k & pmask) == prefix;
                 const int bin = (int)((k >> shift) & 255);
-                // lanes of the warp that hit the same bin add once (integer counts: order-free, deterministic)
-                const unsigned peers = __match_any_sync(__activemask(), in ? bin : -1 - (int)(tid & 31));
-                if (in && (int)(tid & 31) == __ffs(peers) - 1) atomicAdd(&mine[bin], __popc(peers));
+                // integer counts: order-free, deterministic.  When every matching lane of the warp hits the same bin
+                // (the leading bytes of one layer's similarities) one lane adds the population count; otherwise the
+                // lanes add to the warp's private histogram (conflicts are at most 32-way and rare in the low bytes)
+                const unsigned act = __activemask();
+                const unsigned inm = __ballot_sync(act, in);
+                if (inm == 0) continue;
+                const int lead = __ffs(inm) - 1;
+                const int bin0 = __shfl_sync(act, bin, lead);
+                if (__all_sync(act, !in || bin == bin0)) {
+                    if ((int)(tid & 31) == lead) atomicAdd(&mine[bin0], __popc(inm));
+                } else if (in) {
+                    atomicAdd(&mine[bin], 1);
+                }
             }
         }
         __syncthreads();
+        // thread t < 256 owns bin 255 - t: the exclusive prefix of the reversed histogram is the number of keys in HIGHER
+        // bins, so the bin holding the need-th largest key is found by all bins at once (no serial walk by one thread)
+        int mycount = 0;
         if (tid < 256) {
-            int acc = 0;
 #pragma unroll 8
-            for (int w = 0; w < SEL_THREADS / 32; ++w) acc += whist[w][tid];
-            hist[tid] = acc;
+            for (int w = 0; w < SEL_THREADS / 32; ++w) mycount += whist[w][255 - tid];
         }
-        __syncthreads();
-        if (tid == 0) {
-            int acc = 0, bin = 255;
-            for (; bin > 0; --bin) {
-                if (acc + hist[bin] >= need) break;
-                acc += hist[bin];
-            }
-            s_prefix = prefix | ((uint32_t)bin << shift);
-            s_need = need - acc;
+        int tot_unused;
+        const int above = block_excl_scan_1024(mycount, wsum, &tot_unused);
+        if (tid < 256 && above < need && need <= above + mycount) {
+            s_prefix = prefix | ((uint32_t)(255 - tid) << shift);
+            s_need = need - above;
         }
         __syncthreads();
         prefix = s_prefix;

@@ -211,8 +211,22 @@ class ShardedLayer:
         split = [i for i, o in enumerate(owner) if o < 0]
         if split and use_ssr and not _lib.comm_ready():
             init_comm(ctx)                                   # row-sharded SSR all-reduces inside the C sweep loop
-        states = []
-        for (_, W, X) in linears:
+        # Token counts first (one tiny all-reduce while the GPU is idle: no host wait behind the Hessian kernels later).
+        tokens = [X.numel() // X.shape[-1] for _, _, X in linears]
+        if ctx.world > 1:
+            counts = torch.tensor(tokens, dtype=torch.int64, device=ctx.device)
+            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=ctx.group)
+            tokens = counts.tolist()
+        # Hessians widest first, each handed to NCCL the moment its kernel is enqueued (async: the caller's stream goes on
+        # with the next Hessian while the reduction of the previous one crosses NVLink).  The widest input belongs to the
+        # longest chain -- from 4 GPUs up the row-split down_proj, whose inverse is the layer's critical path -- so its
+        # owner can start inverting while the remaining Hessians are still being accumulated.
+        if not hasattr(self, "_join_stream"):
+            self._join_stream = torch.cuda.Stream(ctx.device, priority=-1)
+        js = self._join_stream
+        states, ready = [None] * len(linears), [None] * len(linears)
+        for i in sorted(range(len(linears)), key=lambda i: (-linears[i][2].shape[-1], i)):
+            _, W, X = linears[i]
             st = HessianState(X.shape[-1], ctx.device)
             if hess_timing is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -221,36 +235,39 @@ class ShardedLayer:
             if hess_timing is not None:
                 e1.record()
                 hess_timing.append((e0, e1, X.numel() // X.shape[-1], X.shape[-1]))
-            states.append(st)
-        mark("hessians")
-        if ctx.world > 1:
-            counts = torch.tensor([st.nsamples for st in states], dtype=torch.int64, device=ctx.device)
-            dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=ctx.group)
-            # widest first: the longest chain's Hessian lands on its owner first
-            for i in sorted(range(len(states)), key=lambda i: (-states[i].columns, i)):
+            ev = torch.cuda.Event()
+            if ctx.world > 1:
                 if owner[i] < 0:
-                    dist.all_reduce(states[i].H, op=dist.ReduceOp.SUM, group=ctx.group)
+                    work = dist.all_reduce(st.H, op=dist.ReduceOp.SUM, group=ctx.group, async_op=True)
                 else:
-                    dist.reduce(states[i].H, dst=owner[i], op=dist.ReduceOp.SUM, group=ctx.group)
-            for st, c in zip(states, counts.tolist()):
-                st.nsamples = int(c)
-                st._cache.clear()
-        mark("reduce")
+                    work = dist.reduce(st.H, dst=owner[i], op=dist.ReduceOp.SUM, group=ctx.group, async_op=True)
+                with torch.cuda.stream(js):
+                    work.wait()                                  # js waits for NCCL's stream, the host does not
+                    ev.record(js)
+                st.H.record_stream(js)
+            else:
+                ev.record(main)
+            st.nsamples = int(tokens[i])
+            st._cache.clear()
+            states[i], ready[i] = st, ev
+        mark("hessians")
+        mark("reduce", js if ctx.world > 1 else main)
         # split linears first on their owner: the inverse is the longest single dependent chain of the layer
         pending = {}
         if split:
             if not hasattr(self, "_inv_stream"):
-                self._inv_stream = torch.cuda.Stream(ctx.device)
-            self._inv_stream.wait_stream(main)
+                self._inv_stream = torch.cuda.Stream(ctx.device, priority=-3)
             for i in split:
                 st, m = states[i], states[i].columns
                 if -1 - owner[i] == ctx.rank:
+                    self._inv_stream.wait_event(ready[i])        # this Hessian's all-reduce only, not the later Hessians
                     with torch.cuda.stream(self._inv_stream):
                         Hd, Hinv, info = st.damped_inverse(self.percdamp)
                         done = torch.cuda.Event()
                         done.record(self._inv_stream)
                         mark("split_inverse", self._inv_stream)
                 else:
+                    main.wait_event(ready[i])
                     Hd = st.damped(self.percdamp)
                     Hinv = torch.empty((m, m), dtype=torch.float32, device=ctx.device)
                     info = torch.zeros(1, dtype=torch.int32, device=ctx.device)
@@ -264,7 +281,8 @@ class ShardedLayer:
             if not torch.is_tensor(W):
                 raise ValueError(f"{linears[i][0]}: this rank owns the linear and needs its weight, not just the shape")
             gs.append(GPTQ(LinearView(W), self.block_size, self.percdamp, hessian=states[i]))
-        chain_seq = self._driver.enqueue_chains(gs, use_ssr=use_ssr, aga=aga, max_iter=max_iter, order=order)
+        chain_seq = self._driver.enqueue_chains(gs, use_ssr=use_ssr, aga=aga, max_iter=max_iter, order=order,
+                                                ready=[ready[i] for i in mine])
         # split linears: inverse broadcast, then every rank sweeps its row slab (statistics all-reduced per block)
         slabs = {}
         for i in split:
