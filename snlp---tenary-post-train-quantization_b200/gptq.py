@@ -223,6 +223,21 @@ class GPTQ:
 
         def run(hinv):
             W = self.layer.weight.data.detach().to(torch.float32).clone().contiguous()     # gptq.py:91
+            hd, hraw, code, sperm = Hd, self.state.H, order_code, static_perm
+            if order == "actorder":
+                # A fixed sweep order is the sequential sweep of the problem with its columns permuted up front (the
+                # extension's own definition).  Doing the permutation physically -- one gather of W and of the
+                # Hessian matrices -- keeps every block step on contiguous columns: the feedback GEMM then takes its TMA
+                # epilogue instead of a 4-byte-granular gather through an arbitrary permutation (measured at 5120 x 13824:
+                # 2.4 ms per block step gathered, vs ~0.1 ms contiguous).  Same values, same operation order: same bits.
+                p64 = static_perm.long()
+                W = W.index_select(1, p64).contiguous()
+                hinv = hinv.index_select(0, p64).index_select(1, p64).contiguous()
+                if aga == "hessian":
+                    hd = Hd.index_select(0, p64).index_select(1, p64).contiguous()
+                elif aga == "activations":
+                    hraw = self.state.full().index_select(0, p64).index_select(1, p64).contiguous()
+                code, sperm = _lib.ORDER_SEQUENTIAL, None
             T8 = torch.empty((n, m), dtype=torch.int8, device=dev)
             alpha = torch.empty((n, nb), dtype=torch.float32, device=dev)
             mu = torch.empty((n, nb), dtype=torch.float32, device=dev)
@@ -230,13 +245,18 @@ class GPTQ:
             ws_bytes = lib.tq_sweep_workspace_bytes(n, m, b)
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
             with torch.cuda.device(dev):
-                _lib.check(lib.tq_sweep_layer(_lib.ptr(W), W.stride(0), n, m, _lib.ptr(Hd), _lib.ptr(self.state.H),
-                                              _lib.ptr(hinv), b, order_code, _AGA[aga], int(max_iter),
-                                              _lib.ptr(static_perm), _lib.ptr(T8), _lib.ptr(alpha), _lib.ptr(mu),
+                _lib.check(lib.tq_sweep_layer(_lib.ptr(W), W.stride(0), n, m, _lib.ptr(hd), _lib.ptr(hraw),
+                                              _lib.ptr(hinv), b, code, _AGA[aga], int(max_iter),
+                                              _lib.ptr(sperm), _lib.ptr(T8), _lib.ptr(alpha), _lib.ptr(mu),
                                               _lib.ptr(perm), _lib.ptr(ws), ws_bytes, int(self.sweep_flags), _lib.stream()),
                            "tq_sweep_layer")
-            for t in (W, ws):
-                t.record_stream(torch.cuda.current_stream(dev))
+            for t in (W, ws, hinv, hd, hraw):
+                if t is not None:
+                    t.record_stream(torch.cuda.current_stream(dev))
+            if order == "actorder":
+                # codes back to ORIGINAL column positions (gptq.py:155); block k of alpha / mu belongs to perm[128k : 128k+128]
+                T8 = torch.empty_like(T8).index_copy_(1, static_perm.long(), T8)
+                perm = static_perm
             return alpha, mu, T8, perm
 
         self._pending = (run, Hd, info, run(Hinv), torch.cuda.current_stream(dev))
