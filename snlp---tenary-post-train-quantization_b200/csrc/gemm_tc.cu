@@ -585,7 +585,8 @@ split_kernel(const float* __restrict__ in, int64_t ld_in, int rows, int cols, fl
 
 // B operand of the error feedback, K-major:  coef[j][i] = Hinv[blk_i, rem_j] / clamp(Hinv[blk_i, blk_i], 1e-8)
 // (gptq.py:173-181), written as hi/lo.  Reads walk rem_j (ascending, near-contiguous) along rows blk_i of Hinv.
-constexpr int COEF_SPAN = 4;          // 32-position sub-tiles per CTA: one partial of C 1 per 128 remaining positions
+constexpr int COEF_SPAN = 1;          // 32-position sub-tiles per CTA (4 was tried: fewer partials of C 1 for the fold in
+                                      // aga_vector_kernel, 23 -> 22 us, but this kernel went 6 -> 15 us)
 __global__ void __launch_bounds__(256)
 feedback_coef_kernel(const float* __restrict__ Hinv, int64_t ldh, const int32_t* __restrict__ blk_idx, int blk0, int b,
                      const int32_t* __restrict__ rem_idx, int rem0, int rem, float* __restrict__ hi,

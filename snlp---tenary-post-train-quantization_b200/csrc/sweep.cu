@@ -194,7 +194,7 @@ extern "C" int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const
         }
         const float* s1d = (aga != TQ_AGA_NONE) ? ws.s1d : nullptr;
         if ((rc = launch_aga_vector(Haga, m, blk_idx, done, b, aga, ws.s1d, emit_stats ? ws.csum_part : nullptr,
-                                    ceil_div(rem, 128), emit_stats ? ws.csum : nullptr, st)))
+                                    ceil_div(rem, 32), emit_stats ? ws.csum : nullptr, st)))
             return rc;
         if ((rc = launch_atq_block(W, ldw, n, blk_idx, done, b, s1d, max_iter, ws.Tperm + done, m, alpha + k, mu + k,
                                    nb, ws.E, tc_feedback ? ws.E_lo : nullptr, ldb, nullptr,

@@ -137,6 +137,28 @@ class HessianState:
         return self._cache[key]
 
 
+def _exact_feedback_matrix(Hinv: torch.Tensor, static_perm: Optional[torch.Tensor], block: int) -> torch.Tensor:
+    """Coefficient source of the OBS-exact block feedback, in SWEEP order.
+
+    With U the upper Cholesky factor of H^-1 in sweep order (H^-1 = U'U), the inverse Hessian of the problem that remains
+    after the first k blocks is U_RR' U_RR, and the exact update of the remaining columns R after block B is
+    dW_R = -E_B (Hc_BB)^-1 Hc_BR = -E_B U_BB^-1 U_BR.  The sweep's coefficient kernel forms G[blk, rem] / G[blk, blk]
+    (gptq.py:173-181), so the matrix handed to it is G with unit diagonal and G[B, R] = U_BB^-1 U_BR per block: one
+    Cholesky factorisation and one triangular solve per block (library calls on the GPU, prologue only; default off)."""
+    m = Hinv.shape[0]
+    Hp = Hinv
+    if static_perm is not None:
+        p64 = static_perm.long()
+        Hp = Hinv.index_select(0, p64).index_select(1, p64)
+    U = torch.linalg.cholesky(Hp.double(), upper=True)
+    G = torch.eye(m, dtype=torch.float64, device=Hinv.device)
+    for k0 in range(0, m, block):
+        k1 = min(k0 + block, m)
+        if k1 < m:
+            G[k0:k1, k1:] = torch.linalg.solve_triangular(U[k0:k1, k0:k1], U[k0:k1, k1:], upper=True)
+    return G.float().contiguous()
+
+
 class GPTQ:
     """gptq.py:21-230."""
 
@@ -188,15 +210,21 @@ class GPTQ:
 
     @torch.no_grad()
     def quantize(self, use_ssr: bool = True, aga: str = "hessian", order: Optional[str] = None,
-                 max_iter: int = 100) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
+                 max_iter: int = 100, feedback: str = "reference",
+                 dead_columns: bool = False) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
         """gptq.py:78-199.  New optional arguments keep the reference's behaviour by default:
         aga   'hessian' (gptq.py:147-150) | 'activations' (main.py:177-180) | 'none'
-        order None -> 'ssr' if use_ssr else 'sequential'; 'actorder' = descending diag(H) (extension)."""
-        self.enqueue(use_ssr=use_ssr, aga=aga, order=order, max_iter=max_iter)
+        order None -> 'ssr' if use_ssr else 'sequential'; 'actorder' = descending diag(H) (extension).
+        Canonical-GPTQ exactness options (they sit where the reference has gptq.py:158-186):
+        feedback 'reference' = rows of the static H^-1 over its diagonal (gptq.py:173-181) |
+                 'block_exact' = the OBS-exact block update through the Cholesky factor of H^-1 (static orders only)
+        dead_columns  True: inputs that are identically zero in the calibration data get H_jj = 1 and weight 0."""
+        self.enqueue(use_ssr=use_ssr, aga=aga, order=order, max_iter=max_iter, feedback=feedback, dead_columns=dead_columns)
         return self.finish()
 
     @torch.no_grad()
-    def enqueue(self, use_ssr: bool = True, aga: str = "hessian", order: Optional[str] = None, max_iter: int = 100):
+    def enqueue(self, use_ssr: bool = True, aga: str = "hessian", order: Optional[str] = None, max_iter: int = 100,
+                feedback: str = "reference", dead_columns: bool = False):
         """Asynchronous half of quantize(): enqueue prologue (scale + damp, Cholesky inverse) and the whole
         column sweep on the CURRENT stream and return without touching the host again.  finish() must follow.
         A layer driver enqueues several linears on different streams before finishing any of them."""
@@ -207,15 +235,30 @@ class GPTQ:
             order = "ssr" if use_ssr else "sequential"
         if order not in ("ssr", "sequential", "actorder"):
             raise ValueError("order must be 'ssr', 'sequential' or 'actorder'")
+        if feedback not in ("reference", "block_exact"):
+            raise ValueError("feedback must be 'reference' or 'block_exact'")
+        if feedback == "block_exact" and order == "ssr":
+            raise ValueError("feedback='block_exact' needs a static sweep order ('sequential' or 'actorder'): the exact "
+                             "recursion eliminates columns in an order known up front")
         n, m, b = self.rows, self.columns, self.block_size
         dev = self.device
         nb = (m + b - 1) // b
 
+        state, dead = self.state, None
+        if dead_columns:
+            # canonical GPTQ: dead = diag(H) == 0; H[dead, dead] = 1; W[:, dead] = 0.  Applied to a private copy of the
+            # accumulator (the state may be shared with other linears) and without a host round trip.
+            Hfull = self.state.full()
+            dead = torch.diagonal(Hfull) == 0
+            state = HessianState(m, dev)
+            state.H = Hfull.clone()
+            torch.diagonal(state.H).masked_fill_(dead, float(self.state.nsamples))      # = 1 after the 1 / nsamples scaling
+            state.nsamples = self.state.nsamples
         if aga == "activations":
             # the AGA Gram reads H[blk, blk] on both sides of the diagonal: mirror the tcgen05 SYRK's upper tiles BEFORE the
             # inverse is enqueued (its cache event then also covers the mirroring for linears sharing this Hessian)
-            self.state.full()
-        Hd, Hinv, info = self.state.damped_inverse(self.percdamp)
+            state.full()
+        Hd, Hinv, info = state.damped_inverse(self.percdamp)
         static_perm = None
         order_code = {"ssr": _lib.ORDER_SSR, "sequential": _lib.ORDER_SEQUENTIAL, "actorder": _lib.ORDER_STATIC}[order]
         if order == "actorder":
@@ -223,7 +266,11 @@ class GPTQ:
 
         def run(hinv):
             W = self.layer.weight.data.detach().to(torch.float32).clone().contiguous()     # gptq.py:91
-            hd, hraw, code, sperm = Hd, self.state.H, order_code, static_perm
+            if dead is not None:
+                W.masked_fill_(dead.unsqueeze(0), 0.0)
+            hd, hraw, code, sperm = Hd, state.H, order_code, static_perm
+            if feedback == "block_exact":
+                hinv = _exact_feedback_matrix(hinv, static_perm, b)          # in sweep order when static_perm is given
             if order == "actorder":
                 # A fixed sweep order is the sequential sweep of the problem with its columns permuted up front (the
                 # extension's own definition).  Doing the permutation physically -- one gather of W and of the
@@ -232,11 +279,12 @@ class GPTQ:
                 # 2.4 ms per block step gathered, vs ~0.1 ms contiguous).  Same values, same operation order: same bits.
                 p64 = static_perm.long()
                 W = W.index_select(1, p64).contiguous()
-                hinv = hinv.index_select(0, p64).index_select(1, p64).contiguous()
+                if feedback != "block_exact":                                # (the exact matrix is built in sweep order)
+                    hinv = hinv.index_select(0, p64).index_select(1, p64).contiguous()
                 if aga == "hessian":
                     hd = Hd.index_select(0, p64).index_select(1, p64).contiguous()
                 elif aga == "activations":
-                    hraw = self.state.full().index_select(0, p64).index_select(1, p64).contiguous()
+                    hraw = state.full().index_select(0, p64).index_select(1, p64).contiguous()
                 code, sperm = _lib.ORDER_SEQUENTIAL, None
             T8 = torch.empty((n, m), dtype=torch.int8, device=dev)
             alpha = torch.empty((n, nb), dtype=torch.float32, device=dev)
@@ -259,6 +307,7 @@ class GPTQ:
                 perm = static_perm
             return alpha, mu, T8, perm
 
+        self._sweep_state = state
         self._pending = (run, Hd, info, run(Hinv), torch.cuda.current_stream(dev))
 
     @torch.no_grad()
@@ -276,10 +325,11 @@ class GPTQ:
         if self.info != 0:
             with torch.cuda.stream(stream):
                 Hinv = torch.linalg.pinv(Hd)          # library SVD, as in the reference
-                self.state._cache[float(self.percdamp)] = (Hd, Hinv, torch.zeros_like(info))
+                st = getattr(self, "_sweep_state", None) or self.state
+                st._cache[float(self.percdamp)] = (Hd, Hinv, torch.zeros_like(info))
                 ev = torch.cuda.Event()
                 ev.record(stream)
-                self.state._cache_events[float(self.percdamp)] = (ev, stream)
+                st._cache_events[float(self.percdamp)] = (ev, stream)
                 alpha, mu, T8, perm = run(Hinv)
             stream.synchronize()
         self.alpha = alpha.to(self.dtype)

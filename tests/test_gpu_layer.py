@@ -274,3 +274,52 @@ def test_non_pd_hessian_takes_the_pinv_route(tag, golden_dir):
     q2 = tq100.GPTQ(_layer(W), block_size=128, percdamp=0.01, hessian=q.state)
     a2, u2, T2, p2 = q2.quantize(use_ssr=(tag == "ssr"))
     assert q2.info == 0 and torch.equal(T2, T) and torch.equal(p2, perm)
+
+
+# ---- canonical-GPTQ exactness options (default off), against oracle/gptq_canonical.py ---------------
+@pytest.mark.parametrize("order", ["sequential", "actorder"])
+def test_block_exact_feedback_vs_oracle(order):
+    """feedback='block_exact': the OBS-exact block update through the Cholesky factor of H^-1, against the oracle's
+    first-principles form (solve with the current inverse Hessian + Schur complement per block).  The two formulations
+    differ in arithmetic (fp64 Schur recursion vs one Cholesky), so parity is judged like every layer test; the
+    reconstruction error must also improve on the reference's own feedback (what the option is for)."""
+    import tq100
+    from oracle import gptq_canonical as gc
+    n, m = 256, 768
+    W = synth.make_weight(n, m, seed=811)
+    X = synth.make_activations(6, 256, m, seed=812, lam=1.0)
+    Xf = X.astype(np.float32).reshape(-1, m)
+    H = Xf.T @ Xf
+    q = tq100.GPTQ(_layer(W))
+    q.add_batch(torch.from_numpy(X).to(DEV))
+    alpha, mu, T, perm = q.quantize(use_ssr=False, order=order, feedback="block_exact")
+    ra, ru, rT, rp = gc.quantize_layer_exact(W, H, Xf.shape[0], 128, 0.01, order, feedback="block_exact")
+    got = dict(alpha=alpha.cpu().numpy(), mu=mu.cpu().numpy(), T=T.cpu().numpy(), perm=perm.cpu().numpy())
+    parity.assert_layer_parity(got, dict(alpha=ra, mu=ru, T=rT, perm=rp), what=f"block_exact/{order}")
+    e_exact = oracle.reconstruction_error(W, q.get_quantized_weight().cpu().numpy(), H)
+    q.quantize(use_ssr=False, order=order)                                         # the reference's feedback, same inputs
+    e_ref = oracle.reconstruction_error(W, q.get_quantized_weight().cpu().numpy(), H)
+    assert e_exact < e_ref, (e_exact, e_ref)
+    with pytest.raises(ValueError):
+        q.quantize(use_ssr=True, feedback="block_exact")                           # needs a static order
+
+
+def test_dead_columns_vs_oracle():
+    """dead_columns=True: input features that never fire (diag(H) == 0) get H_jj = 1 and weight 0 (canonical GPTQ)."""
+    import tq100
+    from oracle import gptq_canonical as gc
+    n, m = 128, 512
+    W = synth.make_weight(n, m, seed=821)
+    X = synth.make_activations(4, 256, m, seed=822, lam=0.5)
+    deadc = np.array([3, 130, 131, 400])
+    X[:, :, deadc] = 0
+    Xf = X.astype(np.float32).reshape(-1, m)
+    H = Xf.T @ Xf
+    q = tq100.GPTQ(_layer(W))
+    q.add_batch(torch.from_numpy(X).to(DEV))
+    alpha, mu, T, perm = q.quantize(use_ssr=False, dead_columns=True)
+    ra, ru, rT, rp = gc.quantize_layer_exact(W, H, Xf.shape[0], 128, 0.01, "sequential", feedback="reference", dead_columns=True)
+    got = dict(alpha=alpha.cpu().numpy(), mu=mu.cpu().numpy(), T=T.cpu().numpy(), perm=perm.cpu().numpy())
+    parity.assert_layer_parity(got, dict(alpha=ra, mu=ru, T=rT, perm=rp), what="dead_columns")
+    # the shared accumulator is untouched, and without the option the zero diagonal stays what the reference makes of it
+    assert float(q.H.diagonal()[3]) == 0.0
