@@ -561,6 +561,47 @@ def layer_sweep_line(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------ N1 leg: whole-model driver at 7B width
+def whole_model_leg(torch, tq100, dev, layers=2, samples=SAMPLES, seq=SEQ):
+    """SURVEY 8f N1 at full width: PT2LLMQuantizer.quantize() -- the reference's main.py:232-311 entry point -- on a
+    llama-shaped stack of `layers` transformer layers at LLaMA-2-7B width (fp16 weights, random init), fed 128 x 2048
+    synthetic calibration tokens.  Everything the per-linear bench leaves out is inside: one capture forward per sample,
+    two layer forwards per layer and sample, Hessians streamed from forward hooks (one tq_hessian_accum per sample and
+    distinct input), shared Hessians for q/k/v and gate/up, AGA on the activation Gram (main.py:177-180), the
+    dequantised weights written back, every result copied to the host.  Activations never leave the GPU, so this is
+    the compute-bound form of the end-to-end story (the `e2e` leg streams 12 GB of stored activations per layer over
+    PCIe instead)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import toy_model
+    torch.manual_seed(0)
+    lm = toy_model.ToyLM(vocab=512, d=LLAMA2_7B["d"], ffn=LLAMA2_7B["ffn"], layers=layers).to(dev)
+    with torch.no_grad():
+        for name, p in lm.named_parameters():
+            if p.dim() == 2:
+                p.normal_(0.0, 0.02 if "embed" not in name else 1.0)
+    lm = lm.half().eval()
+    gen = torch.Generator().manual_seed(3)
+    toks = [torch.randint(0, 512, (1, seq), generator=gen) for _ in range(samples)]
+    w0 = {k: v.clone() for k, v in lm.state_dict().items()}
+    dt = None
+    for attempt in range(2):                    # the first pass warms cuBLAS / the allocator; the second is reported
+        lm.load_state_dict(w0)
+        pq = tq100.PT2LLMQuantizer(lm, None, model_type="llama", use_ssr=True, device=dev)
+        before = tq100._lib.launch_count()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        params = pq.quantize(toks)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    return {"value": dt, "unit": "s", "layers": layers, "per_layer_s": dt / layers,
+            "whole_model_estimate_s": dt / layers * LLAMA2_7B["layers"], "linears": len(params),
+            "layer_forwards": int(pq.layer_forwards), "gpu_launches": int(tq100._lib.launch_count() - before),
+            "note": f"PT2LLMQuantizer.quantize on {layers} llama-shaped layers at 7B width, {samples} x {seq} tokens, "
+                    "fp16 model, SSR, hook-streamed Hessians (4 per layer), results on the host; wall clock; the estimate "
+                    "multiplies the per-layer time by 32 (every layer has the same shapes); second of two passes.  About half of the "
+                    "time is the model's own fp16 forwards (2 per layer and sample), which the per-linear legs do not contain"}
+
+
 # ------------------------------------------------------------------------------------ N2 leg
 def packed_layer_leg(torch, tq100, dev):
     n = m = 4096
@@ -632,6 +673,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-shared", action="store_true", help="skip the secondary shared-Hessian (N1) measurement")
     ap.add_argument("--no-packed", action="store_true", help="skip the secondary packed-layer (N2) measurement")
+    ap.add_argument("--no-whole-model", action="store_true", help="skip the secondary whole-model (N1) measurement")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip the same-box reference-on-CUDA leg (and the parity it feeds)")
     ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
@@ -914,6 +956,13 @@ def main():
         except Exception as exc:                                   # secondary measurement: never lose the headline line
             n2 = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
+    n1_model = None
+    if world == 1 and not args.no_whole_model and args.config == "7b-ssr":
+        try:
+            n1_model = whole_model_leg(torch, tq100, dev)
+        except Exception as exc:
+            n1_model = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     if rank == 0:
         line = {"metric": METRIC[args.config], "value": value, "unit": "s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
@@ -928,6 +977,8 @@ def main():
             line["n1_shared_inputs"] = n1
         if n2 is not None:
             line["n2_packed_layer"] = n2
+        if n1_model is not None:
+            line["n1_whole_model"] = n1_model
         line["dtype_note"] = "fp32 arithmetic; fp16 activations enter the tensor cores exactly, fp32 accumulate"
         if ref_cuda is not None:
             line["reference_cuda"] = ref_cuda
