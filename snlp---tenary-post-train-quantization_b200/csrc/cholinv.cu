@@ -82,9 +82,10 @@ __device__ __forceinline__ void diag_factor_invert_32(float* S, float* V, float*
             const float4 t = *reinterpret_cast<const float4*>(cb + 4 * v);
             lc[4 * v] = t.x; lc[4 * v + 1] = t.y; lc[4 * v + 2] = t.z; lc[4 * v + 3] = t.w;
         }
-        // a[t] holds column j + t of this row: update columns j + t <= row (t <= rel) and shift left
+        // a[t] holds column j + t of this row: rank-1 update and shift left.  No predicate: for t > rel the entry lies above
+        // the diagonal of its row, is never read (the stored column is forced to 0 there, rows above the pivot have l = 0)
 #pragma unroll
-        for (int t = 1; t < SB; ++t) a[t - 1] = (t <= rel) ? fmaf(-l, lc[t], a[t]) : a[t];
+        for (int t = 1; t < SB; ++t) a[t - 1] = fmaf(-l, lc[t], a[t]);
         a[SB - 1] = 0.f;
     }
     __syncwarp();
@@ -99,13 +100,11 @@ __device__ __forceinline__ void diag_factor_invert_32(float* S, float* V, float*
     for (int i = 0; i < SB; ++i) {
         const float x = acc[0] * rdiag[i];                   // 0 for i < q: nothing has reached the accumulator yet
         vcol[i * CB_LD] = x;
-        const float* lcol = S + (o + i) * CB_LD + o + i;     // L[i + t][i] at lcol[t * CB_LD] (zero rows past the block are
-                                                             // never read: t <= 31 - i is enforced by the clamp below)
+        // L[i + t][i] at lcol[t * CB_LD]: constant offsets, no index arithmetic.  Rows past the sub-block (i + t >= 32) read
+        // whatever follows in shared memory (S is followed by V and P: in bounds) into accumulators that are never used.
+        const float* lcol = S + (o + i) * CB_LD + o + i;
 #pragma unroll
-        for (int t = 1; t < SB; ++t) {
-            const int tt = (i + t < SB) ? t : 0;             // clamp: rows past the sub-block contribute nothing useful
-            acc[t - 1] = fmaf(-lcol[tt * CB_LD], x, acc[t]);
-        }
+        for (int t = 1; t < SB; ++t) acc[t - 1] = fmaf(-lcol[t * CB_LD], x, acc[t]);
         acc[SB - 1] = 0.f;
     }
 }
@@ -269,9 +268,17 @@ chol_diag_kernel(float* __restrict__ A, int64_t ld, int m, int k0, float* __rest
 #undef TQ_PROF
 }
 
-// L_ik = A_ik D_k'   (rows below the panel), in place
+// L_ik = A_ik D_k'   (rows below the panel), in place; when split_hi / split_lo are given the solved panel is also written
+// as the (hi, lo) tf32 operand pair of the tensor-core updates (row r - (k0 + CB) of the panel's slot in the stacked split
+// arrays, pitch CB) -- one launch less on the per-panel critical path than a separate split pass
+__device__ __forceinline__ float trsm_rn_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return __uint_as_float(r);
+}
 __global__ void __launch_bounds__(GT_THREADS, 2)
-chol_trsm_kernel(float* __restrict__ A, int64_t ld, int m, int k0, const float* __restrict__ Dk) {
+chol_trsm_kernel(float* __restrict__ A, int64_t ld, int m, int k0, const float* __restrict__ Dk,
+                 float* __restrict__ split_hi, float* __restrict__ split_lo) {
     __shared__ GemmSmem sm;
     const int nb = min(CB, m - k0);
     const int i0 = k0 + CB + blockIdx.x * GT_M;
@@ -289,6 +296,14 @@ chol_trsm_kernel(float* __restrict__ A, int64_t ld, int m, int k0, const float* 
         for (int j = 0; j < 8; ++j) {
             const int c = gt_col(tx, j);
             if (c < nb) A[(int64_t)r * ld + k0 + c] = acc[i][j];
+            if (split_hi != nullptr && c < CB) {
+                // columns past a ragged panel (c >= nb) are zero operands, exactly what the separate split pass left there
+                const float v = (c < nb) ? acc[i][j] : 0.f;
+                const float h = trsm_rn_tf32(v);
+                const int64_t o = (int64_t)(r - (k0 + CB)) * CB + c;
+                split_hi[o] = h;
+                split_lo[o] = trsm_rn_tf32(__fsub_rn(v, h));
+            }
         }
     }
 }
@@ -520,11 +535,10 @@ extern "C" int tq_chol_inverse(float* Hinv, const float* Hd, int64_t m, float* w
         TQ_LAUNCH_CHECK("chol_diag_kernel");
         if (below > 0) {
             const int tiles = (int)ceil_div(below, GT_M);
-            chol_trsm_kernel<<<tiles, GT_THREADS, 0, st>>>(L, ld, M, k0, Dk);
+            const bool want_split = tc_potrf || tc_trtri;
+            chol_trsm_kernel<<<tiles, GT_THREADS, 0, st>>>(L, ld, M, k0, Dk, want_split ? Sh + off * CB : nullptr,
+                                                           want_split ? Sl + off * CB : nullptr);
             TQ_LAUNCH_CHECK("chol_trsm_kernel");
-            if (tc_potrf || tc_trtri)
-                if ((rc = launch_split(L + (int64_t)(k0 + CB) * ld + k0, ld, below, CB, Sh + off * CB, Sl + off * CB, CB, 0, st)))
-                    return rc;
         }
         if (aux) {
             TQ_CUDA(cudaEventRecord(chol_event(3 * k), st));
