@@ -284,77 +284,73 @@ __global__ void __launch_bounds__(1024)
 aga_vector_kernel(const float* __restrict__ Hsrc, int64_t ldh, const int32_t* __restrict__ blk_idx, int col0,
                   int b, int mode, float* __restrict__ s1d, const float* __restrict__ csum_part, int csum_parts,
                   double* __restrict__ csum) {
+    // One CTA, run once per block step: the code is kept SMALL on purpose (rolled loops, no per-row unrolling) -- the first
+    // version compiled to 5 800 straight-line instructions and spent its 27 us fetching them (ncu: 47 k cycles for 40 k
+    // warp instructions, profiles/r02a notes in DESIGN section 3).
     extern __shared__ float sh[];           // cols[b] (as int), u[b], s1[b]
     int* cols = reinterpret_cast<int*>(sh);
     float* u = sh + b;
     float* s1 = sh + 2 * b;
     __shared__ float red[32];
+    __shared__ double fold[1024];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    // (independent of the AGA vector) fold the coefficient kernel's per-CTA partials of C 1 in a fixed order
-    // (blockDim / b threads per column take interleaved partials, then one thread adds their sums in order: the serial
-    // chain is csum_parts / 8 loads long instead of csum_parts)
+    for (int p = threadIdx.x; p < b; p += blockDim.x) cols[p] = blk_idx ? blk_idx[p] : col0 + p;
+    // (independent of the AGA vector) fold the coefficient kernel's per-CTA partials of C 1 in a fixed order:
+    // blockDim / b threads per column take interleaved partials (eight loads in flight), one thread adds their sums
     if (csum != nullptr) {
-        __shared__ double fold[1024];
         const int subs = max(1, (int)blockDim.x / b);
         const int sub = threadIdx.x / b, i = threadIdx.x - sub * b;
         if (sub < subs) {
-            // eight loads in flight per thread, added in the fixed order t = sub, sub + subs, ... (one L2 round trip per
-            // eight partials instead of one per partial: the fold was the longest part of this kernel at rem ~ 10^4)
             double s = 0.0;
             int t = sub;
+#pragma unroll 1
             for (; t + 7 * subs < csum_parts; t += 8 * subs) {
                 float v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = csum_part[(int64_t)(t + u * subs) * b + i];
+                for (int q = 0; q < 8; ++q) v[q] = csum_part[(int64_t)(t + q * subs) * b + i];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) s += (double)v[u];
+                for (int q = 0; q < 8; ++q) s += (double)v[q];
             }
+#pragma unroll 1
             for (; t < csum_parts; t += subs) s += (double)csum_part[(int64_t)t * b + i];
             fold[sub * b + i] = s;
         }
-        __syncthreads();
-        if (threadIdx.x < b) {
-            double s = 0.0;
-            for (int q = 0; q < subs; ++q) s += fold[q * b + threadIdx.x];
-            csum[threadIdx.x] = s;
-        }
+    }
+    __syncthreads();
+    if (csum != nullptr && threadIdx.x < b) {
+        const int subs = max(1, (int)blockDim.x / b);
+        double s = 0.0;
+#pragma unroll 1
+        for (int q = 0; q < subs; ++q) s += fold[q * b + threadIdx.x];
+        csum[threadIdx.x] = s;
     }
     if (mode == TQ_AGA_NONE) return;
-    for (int p = threadIdx.x; p < b; p += blockDim.x) cols[p] = blk_idx ? blk_idx[p] : col0 + p;
-    __syncthreads();
-    // row-times-vector products of the gathered sub-block; a warp owns rows warp, warp + nwarp, ... and issues the loads
-    // of all of them before reducing (b <= 512: at most 16 rows x 16 elements per lane, usually 4 x 4)
+    // row-times-vector products of the gathered sub-block: warp w owns rows w, w + nwarp, ...; lanes walk the row.
+    // Phase 0: u = Hb 1.  Phase 1 (HESSIAN: S = Hb'Hb, Hb symmetric): s1 = Hb u.
+#pragma unroll 1
     for (int phase = 0; phase < 2; ++phase) {
         if (phase == 1 && mode != TQ_AGA_HESSIAN) break;
-        const float* vec = (phase == 0) ? nullptr : u;
         float* out = (phase == 0) ? u : s1;
-        for (int i0 = warp; i0 < b; i0 += 4 * nwarp) {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-                const int i = i0 + rr * nwarp;
-                if (i < b) {
-                    const float* hrow = Hsrc + (int64_t)cols[i] * ldh;
-                    for (int j = lane; j < b; j += 32) acc[rr] = vec ? fmaf(hrow[cols[j]], vec[j], acc[rr]) : acc[rr] + hrow[cols[j]];
-                }
+#pragma unroll 1
+        for (int i = warp; i < b; i += nwarp) {
+            const float* hrow = Hsrc + (int64_t)cols[i] * ldh;
+            float acc = 0.f;
+#pragma unroll 4
+            for (int j = lane; j < b; j += 32) {
+                const float h = hrow[cols[j]];
+                acc = (phase == 0) ? acc + h : fmaf(h, u[j], acc);
             }
-#pragma unroll
-            for (int rr = 0; rr < 4; ++rr) {
-                const float s = warp_sum(acc[rr]);
-                const int i = i0 + rr * nwarp;
-                if (lane == 0 && i < b) out[i] = s;
-            }
+            acc = warp_sum(acc);
+            if (lane == 0) out[i] = acc;
         }
         __syncthreads();
     }
-    if (mode != TQ_AGA_HESSIAN) {
-        for (int j = threadIdx.x; j < b; j += blockDim.x) s1[j] = u[j];
-        __syncthreads();
-    }
+    const float* res = (mode == TQ_AGA_HESSIAN) ? s1 : u;
     float part = 0.f;
     for (int j = threadIdx.x; j < b; j += blockDim.x) {
-        s1d[j] = s1[j];
-        part += s1[j];
+        const float v = res[j];
+        s1d[j] = v;
+        part += v;
     }
     part = warp_sum(part);
     if (lane == 0) red[warp] = part;
