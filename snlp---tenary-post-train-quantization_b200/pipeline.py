@@ -49,9 +49,12 @@ class LayerDriver:
         prio = os.environ.get("TQ_CHAIN_PRIORITY", "1") != "0"
         self.streams = [torch.cuda.Stream(self.device, priority=((-3 if i == 0 else -1) if prio else 0))
                         for i in range(max(1, num_streams))]
-        # eager: a linear's chain starts as soon as ITS Hessian is complete and overlaps the Hessians still running
-        # (widest input first, so the longest chain starts first); otherwise all chains wait for all Hessians
-        self.eager = (os.environ.get("TQ_EAGER_CHAINS", "1") != "0") if eager_chains is None else bool(eager_chains)
+        # eager: a linear's chain starts as soon as ITS Hessian is complete and overlaps the Hessians still running;
+        # otherwise (default) all chains wait for all Hessians.  Measured on one B200 (8 layers of the 7B bench): eager
+        # 118.9 ms per layer with the Hessian kernels at 1 095 TFLOP/s (the chains' wide kernels take SMs from them),
+        # not eager 114.8 ms with the Hessians at 1 173 TFLOP/s -- the chain phase is bound by its own GEMM launches, not
+        # by when it starts.
+        self.eager = (os.environ.get("TQ_EAGER_CHAINS", "0") != "0") if eager_chains is None else bool(eager_chains)
 
     def quantize(self, linears, use_ssr: bool = True, aga: str = "hessian", max_iter: int = 100, hess_timing=None,
                  order: Optional[str] = None):
