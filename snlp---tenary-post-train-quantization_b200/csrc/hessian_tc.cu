@@ -292,6 +292,194 @@ hessian_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     if (CLUSTER > 1) cluster_sync_all();             // neither CTA leaves while the other may still signal its barriers
 }
 
+
+// ---- 2-SM MMA form (tcgen05 cta_group::2) ---------------------------------------------------------------------------
+// The two CTAs of a cluster issue ONE 256 x 256 x 16 MMA per step between them: CTA r supplies rows [128 r, 128 r + 128)
+// of the A operand and columns [128 r, 128 r + 128) of the B operand from its own shared memory, and receives rows
+// [128 r, ...) of the accumulator in its own TMEM.  Per 64-token step a CTA stages 16 KB of A + 16 KB of B (was 16 + 32):
+// six pipeline stages instead of four in the same shared memory, half the shared-memory operand reads per flop.
+//   producer (warp 0, both CTAs)  TMA `.cta_group::2` loads into the CTA's own stage; the bytes are counted on the LEADER's
+//                                 `full` barrier (peer bit cleared), which the leader arms with both CTAs' 64 KB
+//   MMA (warp 1, leader only)     tcgen05.mma.cta_group::2; tcgen05.commit.cta_group::2 ... multicast frees the stage in
+//                                 both CTAs (`empty`) and publishes the accumulator to both epilogues (`tfull`)
+//   epilogue (warps 4-7, both)    as the single-CTA kernel on the CTA's own 128 rows; every thread arrives on the
+//                                 LEADER's `tempty` (count 256) when it has read its part of the accumulator
+constexpr int HP_STAGES = 6;
+constexpr int HP_STAGE_BYTES = HT_A_BYTES + HT_A_BYTES;            // A 128 x 64 + B half 128 x 64 (bf16 / fp16)
+constexpr int HP_SMEM = HP_STAGES * HP_STAGE_BYTES + HT_EPI_STAGES * HT_EPI_BYTES + 256 + 1024;
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;                          // shared::cluster address of the same offset in CTA 0
+
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit_multicast(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(HT_THREADS, 1)
+hessian_tc_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_h,
+                       int Nt, int kc, const __grid_constant__ TileSched sched, uint32_t idesc) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t s_epi = s_base + HP_STAGES * HP_STAGE_BYTES;
+    const uint32_t s_bar = s_epi + HT_EPI_STAGES * HT_EPI_BYTES;
+    auto full_bar = [&](int s) { return s_bar + 8 * s; };
+    auto empty_bar = [&](int s) { return s_bar + 8 * (HP_STAGES + s); };
+    auto tfull_bar = [&](int a) { return s_bar + 8 * (2 * HP_STAGES + a); };
+    auto tempty_bar = [&](int a) { return s_bar + 8 * (2 * HP_STAGES + 2 + a); };
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + HP_STAGES * HP_STAGE_BYTES + HT_EPI_STAGES * HT_EPI_BYTES + 8 * (2 * HP_STAGES + 4));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_h) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < HP_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * 128); }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int unit = blockIdx.x >> 1;
+
+    const long long total_items = sched.total_items();
+    const long long item0 = (long long)(unit / sched.round_ctas) * sched.round_ctas * sched.items_per_cta +
+                            unit % sched.round_ctas;
+    const int item_stride = sched.round_ctas, my_items = sched.items_per_cta;
+
+    if (warp == 0 && lane == 0) {
+        // ===== TMA producer (both CTAs) =====
+        int stage = 0, phase = 0;
+        for (int ji = 0; ji < my_items; ++ji) {
+            const long long it = item0 + (long long)ji * item_stride;
+            if (it >= total_items) break;
+            int chunk, bi, bj;
+            sched.decode(it, chunk, bi, bj);
+            const int t0 = chunk * kc;
+            const int t1 = min(Nt, t0 + kc);
+            const int nkb = (t1 - t0 + HT_BK - 1) / HT_BK;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1);
+                const uint32_t sa = s_base + stage * HP_STAGE_BYTES;
+                const uint32_t sb = sa + HT_A_BYTES;
+                const uint32_t lbar = full_bar(stage) & PEER_MASK;
+                if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * HP_STAGE_BYTES);   // this CTA's and the peer's bytes
+                const int tok = t0 + kb * HT_BK;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) tma_load_2d_2sm(sa + c * HT_BOX_BYTES, &map_x, lbar, (2 * bi + rank) * HT_BM + c * 64, tok);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) tma_load_2d_2sm(sb + c * HT_BOX_BYTES, &map_x, lbar, bj * HT_BN + rank * 128 + c * 64, tok);
+                if (++stage == HP_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ===== MMA issuer (leader CTA only) =====
+        int stage = 0, phase = 0, n_item = 0;
+        for (int ji = 0; ji < my_items; ++ji, ++n_item) {
+            const long long it = item0 + (long long)ji * item_stride;
+            if (it >= total_items) break;
+            int chunk, bi, bj;
+            sched.decode(it, chunk, bi, bj);
+            const int t0 = chunk * kc;
+            const int t1 = min(Nt, t0 + kc);
+            const int nkb = (t1 - t0 + HT_BK - 1) / HT_BK;
+            const int acc = n_item & 1;
+            mbar_wait(tempty_bar(acc), ((n_item >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * HT_BN;
+            for (int kb = 0; kb < nkb; ++kb) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                const uint32_t sa = s_base + stage * HP_STAGE_BYTES;
+                const uint32_t sb = sa + HT_A_BYTES;
+#pragma unroll
+                for (int k = 0; k < HT_BK / HT_UMMA_K; ++k) {
+                    const uint64_t ad = make_desc(sa + k * HT_UMMA_K * 128);
+                    const uint64_t bd = make_desc(sb + k * HT_UMMA_K * 128);
+                    umma2_f16(tmem_d, ad, bd, idesc, (kb | k) != 0);
+                }
+                umma2_commit_multicast(empty_bar(stage), 0x3);
+                if (kb == nkb - 1) umma2_commit_multicast(tfull_bar(acc), 0x3);
+                if (++stage == HP_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue (both CTAs): TMEM -> registers -> swizzled smem -> TMA reduce-add into H =====
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const bool leader = (warp == 4 && lane == 0);
+        int n_item = 0, estage = 0;
+        for (int ji = 0; ji < my_items; ++ji, ++n_item) {
+            const long long it = item0 + (long long)ji * item_stride;
+            if (it >= total_items) break;
+            int chunk, bi, bj;
+            sched.decode(it, chunk, bi, bj);
+            const int acc = n_item & 1;
+            mbar_wait(tfull_bar(acc), (n_item >> 1) & 1);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * HT_BN;
+            for (int cg = 0; cg < HT_BN / HT_EPI_COLS; ++cg) {
+                uint32_t v[32];
+                tmem_ld_32x32(taddr + cg * HT_EPI_COLS, v);
+                tmem_ld_wait();
+                if (cg == HT_BN / HT_EPI_COLS - 1) {     // accumulator fully read: tell the leader's MMA thread
+                    tc_fence_before();
+                    mbar_arrive_cluster(tempty_bar(acc) & PEER_MASK);
+                }
+                if (leader) bulk_wait_read<HT_EPI_STAGES - 1>();
+                named_bar_sync(1, 128);
+                const uint32_t sdst = s_epi + estage * HT_EPI_BYTES + row * 128;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t a = sdst + ((c ^ (row & 7)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v[4 * c]), "r"(v[4 * c + 1]),
+                                 "r"(v[4 * c + 2]), "r"(v[4 * c + 3])
+                                 : "memory");
+                }
+                fence_proxy_async_smem();
+                named_bar_sync(1, 128);
+                if (leader) {
+                    tma_reduce_add_2d(&map_h, s_epi + estage * HT_EPI_BYTES, bj * HT_BN + cg * HT_EPI_COLS, (2 * bi + rank) * HT_BM);
+                    bulk_commit();
+                }
+                estage ^= 1;
+            }
+        }
+        if (leader) bulk_wait_read<0>();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                              // nobody frees TMEM or leaves while the peer may still use it
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
 // ---- host side ---------------------------------------------------------------------------------
 PFN_tmapEncodeTiled tmap_encode_fn() {
     static PFN_tmapEncodeTiled fn = nullptr;
@@ -338,7 +526,12 @@ int hessian_accum_tcgen05(float* H, int64_t ldh, const void* X, int64_t Nt, int6
         return rc;
 
     // TQ_HESS_CLUSTER=1 selects the single-CTA kernel (48 KB of operands per step and CTA instead of 32 KB)
-    static const int cluster = []() { const char* e = getenv("TQ_HESS_CLUSTER"); return (e && atoi(e) == 1) ? 1 : 2; }();
+    // TQ_HESS_CLUSTER: 1 = single-CTA kernel, 2 = cluster of two with TMA multicast of the shared operand,
+    // 3 = cluster of two issuing one 256 x 256 MMA between them (tcgen05 cta_group::2; default).  Measured at Nt = 262 144,
+    // m = 4096 / 11008, timed alone: 1 094 / 1 107 -> 1 191 / 1 151 -> 1 266 / 1 201 TFLOP/s useful; inside the 7B bench
+    // 1 162 -> 1 259 TFLOP/s (0.83 -> 0.89 of the sustained cuBLAS peak) for variants 2 -> 3.
+    static const int variant = []() { const char* e = getenv("TQ_HESS_CLUSTER"); const int v = e ? atoi(e) : 3; return (v >= 1 && v <= 3) ? v : 3; }();
+    const int cluster = (variant == 1) ? 1 : 2;
     TileSched sched;
     sched.pair = (cluster == 2) ? 1 : 0;
     sched.nbi = (int)ceil_div(ceil_div(m, HT_BM), cluster);
@@ -384,6 +577,7 @@ int hessian_accum_tcgen05(float* H, int64_t ldh, const void* X, int64_t Nt, int6
     if (dyn_smem_pending(attr_mask, dev)) {
         TQ_CUDA(cudaFuncSetAttribute(hessian_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM));
         TQ_CUDA(cudaFuncSetAttribute(hessian_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HT_SMEM));
+        TQ_CUDA(cudaFuncSetAttribute(hessian_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HP_SMEM));
         dyn_smem_done(attr_mask, dev);
     }
     // TQ_HESS_ITEMS_PER_CTA: work items (one <= 2048-token chunk of one 128 x 256 tile, ~9 us) a CTA processes before it
@@ -397,7 +591,7 @@ int hessian_accum_tcgen05(float* H, int64_t ldh, const void* X, int64_t Nt, int6
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)grid);
         cfg.blockDim = dim3(HT_THREADS);
-        cfg.dynamicSmemBytes = HT_SMEM;
+        cfg.dynamicSmemBytes = (variant == 3) ? HP_SMEM : HT_SMEM;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -406,7 +600,13 @@ int hessian_accum_tcgen05(float* H, int64_t ldh, const void* X, int64_t Nt, int6
         attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        TQ_CUDA(cudaLaunchKernelEx(&cfg, hessian_tc_kernel<2>, map_x, map_h, (int)Nt, (int)kc, sched, idesc));
+        if (variant == 3) {
+            // instruction descriptor of the pair MMA: as above with M = 256 (the two CTAs' 128 rows)
+            const uint32_t idesc2 = (idesc & ~(0x1Fu << 24)) | ((uint32_t)(256 >> 4) << 24);
+            TQ_CUDA(cudaLaunchKernelEx(&cfg, hessian_tc_pair_kernel, map_x, map_h, (int)Nt, (int)kc, sched, idesc2));
+        } else {
+            TQ_CUDA(cudaLaunchKernelEx(&cfg, hessian_tc_kernel<2>, map_x, map_h, (int)Nt, (int)kc, sched, idesc));
+        }
     } else {
         hessian_tc_kernel<1><<<grid, HT_THREADS, HT_SMEM, st>>>(map_x, map_h, (int)Nt, (int)kc, sched, idesc);
     }
