@@ -5,19 +5,63 @@
 
 namespace tq {
 
+// inverse of the sweep order: inv[perm[p]] = p
 __global__ void __launch_bounds__(256)
-unpermute_kernel(const int8_t* __restrict__ Tperm, int n, int m, const int32_t* __restrict__ perm,
-                 int8_t* __restrict__ Torig, float* __restrict__ Tf32) {
-    // scatter form: thread handles sweep position p of row r.  Rows are 4-11 KB, so a CTA's writes
-    // to one row merge in L2 before eviction.
-    const int r = blockIdx.y;
-    const int8_t* src = Tperm + (int64_t)r * m;
-    int8_t* dst = Torig + (int64_t)r * m;
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < m; p += gridDim.x * blockDim.x) {
-        const int c = perm[p];
-        const int8_t v = src[p];
-        dst[c] = v;
-        if (Tf32) Tf32[(int64_t)r * m + c] = (float)v;
+invert_perm_kernel(const int32_t* __restrict__ perm, int m, int32_t* __restrict__ inv) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < m) inv[perm[p]] = p;
+}
+
+// Codes from sweep order back to ORIGINAL column positions (gptq.py:155), gather form: a CTA stages rows of the
+// sweep-ordered codes in shared memory (16-byte loads), every thread assembles FOUR consecutive original columns from it and
+// stores one 32-bit word -- coalesced on both sides of HBM.  (The scatter form it replaces stored single bytes at permuted
+// addresses: 45 MB of partial-sector writes, 0.2-1.0 ms per linear.)
+constexpr int UNP_ROWS = 4;
+__global__ void __launch_bounds__(256)
+unpermute_gather_kernel(const int8_t* __restrict__ Tperm, int n, int m, const int32_t* __restrict__ inv,
+                        int8_t* __restrict__ Torig, float* __restrict__ Tf32) {
+    extern __shared__ int8_t rows[];                       // [UNP_ROWS][mp], mp = m rounded up to 16
+    const int mp = (m + 15) & ~15;
+    const int r0 = blockIdx.x * UNP_ROWS;
+    const int nr = min(UNP_ROWS, n - r0);
+    const bool vec = ((m & 15) == 0) && ((reinterpret_cast<uintptr_t>(Tperm) & 15) == 0);
+    for (int rr = 0; rr < nr; ++rr) {
+        const int8_t* src = Tperm + (int64_t)(r0 + rr) * m;
+        if (vec) {
+            const int4* s4 = reinterpret_cast<const int4*>(src);
+            int4* d4 = reinterpret_cast<int4*>(rows + rr * mp);
+            for (int i = threadIdx.x; i < m / 16; i += blockDim.x) d4[i] = s4[i];
+        } else {
+            for (int i = threadIdx.x; i < m; i += blockDim.x) rows[rr * mp + i] = src[i];
+        }
+    }
+    __syncthreads();
+    const bool wvec = ((m & 3) == 0) && ((reinterpret_cast<uintptr_t>(Torig) & 3) == 0);
+    for (int c0 = threadIdx.x * 4; c0 < m; c0 += blockDim.x * 4) {
+        int src_pos[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) src_pos[k] = (c0 + k < m) ? inv[c0 + k] : 0;
+        for (int rr = 0; rr < nr; ++rr) {
+            const int8_t* row = rows + rr * mp;
+            int8_t v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) v[k] = row[src_pos[k]];
+            const int64_t o = (int64_t)(r0 + rr) * m + c0;
+            if (wvec) {
+                const uint32_t w = (uint32_t)(uint8_t)v[0] | ((uint32_t)(uint8_t)v[1] << 8) | ((uint32_t)(uint8_t)v[2] << 16) |
+                                   ((uint32_t)(uint8_t)v[3] << 24);
+                *reinterpret_cast<uint32_t*>(Torig + o) = w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (c0 + k < m) Torig[o + k] = v[k];
+            }
+            if (Tf32) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (c0 + k < m) Tf32[o + k] = (float)v[k];
+            }
+        }
     }
 }
 
@@ -107,11 +151,22 @@ static inline unsigned grid_for(int64_t work, int threads) {
     return (unsigned)g;
 }
 
+// `inv_scratch`: m ints of device scratch for the inverse permutation
 int launch_unpermute(const int8_t* Tperm, int64_t n, int64_t m, const int32_t* perm, int8_t* Torig, float* Tf32,
-                     cudaStream_t st) {
-    dim3 grid((unsigned)(ceil_div(m, 256) < 64 ? ceil_div(m, 256) : 64), (unsigned)n);
-    unpermute_kernel<<<grid, 256, 0, st>>>(Tperm, (int)n, (int)m, perm, Torig, Tf32);
-    TQ_LAUNCH_CHECK("unpermute_kernel");
+                     int32_t* inv_scratch, cudaStream_t st) {
+    invert_perm_kernel<<<(unsigned)ceil_div(m, 256), 256, 0, st>>>(perm, (int)m, inv_scratch);
+    TQ_LAUNCH_CHECK("invert_perm_kernel");
+    const int mp = (int)((m + 15) & ~(int64_t)15);
+    const int smem = UNP_ROWS * mp;
+    static std::atomic<unsigned long long> attr_mask{0};
+    int dev;
+    if (smem > 48 * 1024 && dyn_smem_pending(attr_mask, dev)) {
+        TQ_CUDA(cudaFuncSetAttribute(unpermute_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        dyn_smem_done(attr_mask, dev);
+    }
+    TQ_CHECK_ARG(smem <= 200 * 1024, "unpermute: m = %lld is beyond the staged-row kernel's shared memory", (long long)m);
+    unpermute_gather_kernel<<<(unsigned)ceil_div(n, UNP_ROWS), 256, smem, st>>>(Tperm, (int)n, (int)m, inv_scratch, Torig, Tf32);
+    TQ_LAUNCH_CHECK("unpermute_gather_kernel");
     return 0;
 }
 
@@ -122,7 +177,13 @@ extern "C" int tq_unpermute_codes(const int8_t* Tperm, int64_t n, int64_t m, con
     using namespace tq;
     TQ_CHECK_ARG(Tperm && perm && Torig && n > 0 && m > 0 && n <= 65535 * 1024, "tq_unpermute_codes: bad arguments");
     TQ_CHECK_ARG(Tperm != Torig, "tq_unpermute_codes: in-place not supported");
-    return launch_unpermute(Tperm, n, m, perm, Torig, Tf32, (cudaStream_t)stream);
+    // the inverse permutation needs m ints of scratch: a stream-ordered temporary (the sweep passes its own workspace)
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t* inv = nullptr;
+    TQ_CUDA(cudaMallocAsync(&inv, sizeof(int32_t) * m, st));
+    const int rc = launch_unpermute(Tperm, n, m, perm, Torig, Tf32, inv, st);
+    TQ_CUDA(cudaFreeAsync(inv, st));
+    return rc;
 }
 
 extern "C" int tq_dequant(const float* alpha, const float* mu, int64_t nb, const int8_t* Torig, int64_t n, int64_t m,

@@ -16,7 +16,7 @@ int launch_ssr_select(const float*, int64_t, const float*, int64_t, const float*
                       int32_t*, int32_t*, float*, uint32_t*, cudaStream_t);
 int launch_err_feedback(float*, int64_t, int64_t, const float*, int64_t, const float*, int64_t, const int32_t*,
                         int64_t, int64_t, const int32_t*, int64_t, int64_t, cudaStream_t);
-int launch_unpermute(const int8_t*, int64_t, int64_t, const int32_t*, int8_t*, float*, cudaStream_t);
+int launch_unpermute(const int8_t*, int64_t, int64_t, const int32_t*, int8_t*, float*, int32_t*, cudaStream_t);
 int launch_ssr_fold(const float*, int64_t, const float*, int64_t, int64_t, float*, cudaStream_t);
 bool comm_active();
 int comm_allreduce_sum_f32(float*, int64_t, cudaStream_t);
@@ -223,5 +223,6 @@ extern "C" int tq_sweep_layer(float* W, int64_t ldw, int64_t n, int64_t m, const
         }
         done += b;
     }
-    return launch_unpermute(ws.Tperm, n, m, perm, Torig, nullptr, st);
+    // (the remaining-column lists are dead by now: ws.rem[0] serves as the inverse-permutation scratch)
+    return launch_unpermute(ws.Tperm, n, m, perm, Torig, nullptr, ws.rem[0], st);
 }
