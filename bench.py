@@ -823,16 +823,17 @@ def main():
     achieved = flops / (h_ms * 1e-3) / 1e12 if h_ms > 0 else 0.0
     # DRAM traffic per launch from the committed ncu --set full capture (profiles/r01c_ncu_full_hessian_tc.txt:
     # dram__bytes_read.sum + dram__bytes_write.sum), averaged over the launches of one layer like `achieved`
-    NCU_TRAFFIC = {4096: 3.37e9, 11008: 58.1e9} if world == 1 else {}   # bytes per launch at Nt = 262144, by m
+    NCU_TRAFFIC = {4096: 2.25e9, 11008: 46.4e9} if world == 1 else {}   # bytes per launch at Nt = 262144, by m
     known = [NCU_TRAFFIC[m_] for _, _, t_, m_ in hess_events if m_ in NCU_TRAFFIC and t_ == SAMPLES * SEQ]
     traffic = sum(known) / len(known) if known and len(known) == len(hess_events) else None
     roofline = {"kernel": "hessian_tc_pair_kernel", "bound": "tensor", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                "traffic_note": "mean DRAM bytes per launch (ncu, profiles/r02_ncu_full_hessian_tc.txt, the 2-SM kernel): 3.37 GB "
-                                "at m=4096 (algorithmic minimum 2.21 GB; one L2-resident tile group, X read once, but ~0.5 GB of "
-                                "reduce-add spills; the cluster-multicast variant measured 2.24 GB), 58.1 GB at m=11008 (6.3 GB): "
-                                "H does not fit L2, X is re-read once per 3584-wide tile group and the reduce-adds spill; the "
-                                "kernel is tensor-bound (tensor pipe 78 %, DRAM at 12-27 % of peak)" if traffic else None,
+                "traffic_note": "mean DRAM bytes per launch of the 2-SM kernel (ncu, dram__bytes_read.sum + dram__bytes_write.sum, "
+                                "profiles/r02_hessian_traffic_ncu.txt: single-pass captures): 2.25 GB at m=4096 = 1.02x the algorithmic "
+                                "2.21 GB (one L2-resident tile group, X read once), 46.4 GB at m=11008 (7.4x of 6.3 GB): H does not "
+                                "fit L2, X is re-read once per 3584-wide tile group and the reduce-adds spill (13 GB written).  The "
+                                "multi-pass --set full capture of the same kernel (profiles/r02_ncu_full_hessian_tc.txt) reads 3.37 / "
+                                "58.1 GB.  The kernel is tensor-bound (tensor pipe 78 %, DRAM at 12-27 % of peak)" if traffic else None,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                                if peaks else "fallback 1.4 PFLOP/s sustained",
                 "flops_counted": "useful SYRK flops Nt*m*(m+1) per launch (dense-equivalent 2*Nt*m^2 is 2x)",
