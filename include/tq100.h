@@ -237,7 +237,8 @@ int tq_comm_allreduce_f32(float* buf, int64_t count, void* stream);
  * tq_sweep_layer uses them instead of NCCL.  Setup, once per process: every rank calls tq_comm_p2p_alloc (cudaMalloc of
  * its own buffer, cap_floats >= 2 * widest layer + 1; returns the 64-byte CUDA IPC handle), the handles are all-gathered
  * by the host (torch.distributed), every rank calls tq_comm_p2p_open with the nranks x 64 bytes in rank order.
- * tq_comm_p2p_ready returns the number of ranks (0 = not open).  All ranks must run the same sequence of sharded sweeps. */
+ * tq_comm_p2p_ready returns the number of ranks (0 = not open).  All ranks must run the same sequence of sharded sweeps,
+ * one at a time per process (the mailboxes and the sequence counter are per process, not per stream). */
 int tq_comm_p2p_alloc(int64_t cap_floats, int rank, int nranks, void* handle64_out);
 int tq_comm_p2p_open(const void* handles);
 int tq_comm_p2p_ready(void);
